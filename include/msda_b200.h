@@ -1,0 +1,125 @@
+/*
+ * msda_b200.h -- C ABI of libmsda_b200.so: multi-scale deformable attention
+ * forward + backward, hand-written CUDA for sm_100a (NVIDIA B200).
+ *
+ * This is the drop-in boundary for the reference's only native component.
+ * The two compute entry points replace, one for one, the two functions the
+ * reference exports from its pybind11 extension `MultiScaleDeformableAttention`
+ *   (/root/reference/models/ops/src/vision.cpp:13-16):
+ *
+ *   msda_forward   <->  ms_deform_attn_forward   (src/ms_deform_attn.h:21-39,
+ *                        src/cuda/ms_deform_attn_cuda.cu:20-80)
+ *   msda_backward  <->  ms_deform_attn_backward  (src/ms_deform_attn.h:42-61,
+ *                        src/cuda/ms_deform_attn_cuda.cu:83-153)
+ *
+ * Differences a binder has to know about:
+ *   - plain device pointers and sizes instead of at::Tensor; the CALLER
+ *     allocates outputs (the reference allocates with at::zeros, :54,:121-123).
+ *     Outputs need NOT be zero-initialised: every element is written exactly
+ *     once, including grad_value.
+ *   - the stream is an explicit argument (the reference takes
+ *     at::cuda::getCurrentCUDAStream(), :65,:135); launches are asynchronous,
+ *     the library never synchronises the stream or the device.
+ *   - errors are RETURNED (status code + msda_last_error()); the reference
+ *     swallows launch failures with a printf (ms_deform_im2col_cuda.cuh:948-952).
+ *   - spatial_shapes / level_start_index are consumed on the device as int64,
+ *     exactly as the reference builds them
+ *     (/root/reference/models/deformable_transformer.py:164-165); no host copy.
+ *   - backward needs a scratch workspace (size from
+ *     msda_backward_workspace_bytes) because grad_value is accumulated
+ *     deterministically instead of with floating-point atomics.
+ *
+ * Tensor layouts (contiguous, row-major), names as in the reference:
+ *   value             [N][S][M][D]          value_dtype
+ *   spatial_shapes    [L][2] int64 (H, W)   device memory
+ *   level_start_index [L]    int64          device memory
+ *   sampling_loc      [N][Lq][M][L][P][2]   aux_dtype, (x, y) normalised to [0,1]
+ *   attn_weight       [N][Lq][M][L][P]      aux_dtype
+ *   output, grad_output [N][Lq][M*D]        value_dtype
+ *   grad_value        like value; grad_sampling_loc / grad_attn_weight like
+ *                     sampling_loc / attn_weight
+ *
+ * dtypes: value_dtype in {F32, BF16, F16, F64}; aux_dtype is either equal to
+ * value_dtype or F32 (the natural autocast mix: bf16 values, fp32 locations
+ * and weights).  Arithmetic is fp32 (fp64 for F64).
+ *
+ * im2col_step: kept for signature parity.  The reference processes
+ * min(N, im2col_step) frames per launch and rejects N not divisible by that
+ * (ms_deform_attn_cuda.cu:50-52); this library always uses one launch and
+ * keeps the divisibility check so error behaviour matches.
+ *
+ * Thread safety: no global mutable state besides the thread-local error
+ * string; concurrent calls on different streams are independent as long as
+ * their workspaces are distinct.
+ */
+#ifndef MSDA_B200_H
+#define MSDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_VERSION 100 /* major*100 + minor */
+
+enum msda_dtype { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F16 = 2, MSDA_F64 = 3 };
+
+enum msda_status {
+    MSDA_OK = 0,
+    MSDA_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive size, bad dtype pair */
+    MSDA_ERR_IM2COL_STEP = 2,      /* N % min(N, im2col_step) != 0 (reference :52,:119) */
+    MSDA_ERR_WORKSPACE = 3,        /* workspace missing or too small */
+    MSDA_ERR_CUDA = 4,             /* a CUDA runtime call or launch failed */
+    MSDA_ERR_UNSUPPORTED = 5       /* shape outside what the kernels index (see msda_last_error) */
+};
+
+/* flags for msda_*_ex: tuning / A-B switches, never needed for correctness */
+#define MSDA_FLAG_LINEAR_TILES 1u  /* do not assume queries are pyramid pixels when Lq == S */
+#define MSDA_FLAG_GENERIC 2u       /* force the any-D scalar kernels */
+#define MSDA_FLAG_ATOMIC_GRAD_VALUE 4u /* bench-only: fp32 red.global scatter (NOT deterministic) */
+
+int msda_version(void);
+
+/* Message of the last non-zero status returned on this thread ("" if none). */
+const char *msda_last_error(void);
+
+/* replaces ms_deform_attn_forward (vision.cpp:14) */
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output,
+                 int N, int S, int M, int D, int L, int Lq, int P,
+                 int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream);
+
+int msda_forward_ex(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                    const void *sampling_loc, const void *attn_weight, void *output,
+                    int N, int S, int M, int D, int L, int Lq, int P,
+                    int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
+
+/* Bytes of device scratch msda_backward needs for this problem size. */
+size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P,
+                                     int value_dtype, int aux_dtype);
+
+/* replaces ms_deform_attn_backward (vision.cpp:15) */
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                  void *workspace, size_t workspace_bytes,
+                  int N, int S, int M, int D, int L, int Lq, int P,
+                  int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream);
+
+int msda_backward_ex(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                     void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                     void *workspace, size_t workspace_bytes,
+                     int N, int S, int M, int D, int L, int Lq, int P,
+                     int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
+
+/* Number of kernels the last msda_forward / msda_backward on this thread launched
+ * (bench.py's gpu_launches is counted from this, not guessed). */
+int msda_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H */

@@ -1,0 +1,57 @@
+"""ctypes binding of libmsda_b200.so (include/msda_b200.h).  No fallback of any kind:
+if the library is missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libmsda_b200.so"
+
+F32, BF16, F16, F64 = 0, 1, 2, 3
+FLAG_LINEAR_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE = 1, 2, 4
+
+EXPORTS = (
+    "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",
+    "msda_backward_workspace_bytes", "msda_backward", "msda_backward_ex", "msda_last_launch_count",
+)
+
+_lib = None
+
+
+class MSDAError(RuntimeError):
+    """A non-zero status from the C ABI (the reference raises RuntimeError through AT_ASSERTM)."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MSDAError(
+            f"{LIB_PATH} is missing. Build it with `python -m neurips2023_soc_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for this op.")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    vp, i, u, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
+    dims = [i] * 7
+    lib.msda_version.restype = i
+    lib.msda_last_error.restype = ctypes.c_char_p
+    lib.msda_last_launch_count.restype = i
+    lib.msda_forward.restype = i
+    lib.msda_forward.argtypes = [vp] * 6 + dims + [i, i, i, vp]
+    lib.msda_forward_ex.restype = i
+    lib.msda_forward_ex.argtypes = [vp] * 6 + dims + [i, i, i, vp, u]
+    lib.msda_backward_workspace_bytes.restype = sz
+    lib.msda_backward_workspace_bytes.argtypes = dims + [i, i]
+    lib.msda_backward.restype = i
+    lib.msda_backward.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp]
+    lib.msda_backward_ex.restype = i
+    lib.msda_backward_ex.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp, u]
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().msda_last_error().decode("utf-8", "replace")
+        raise MSDAError(f"libmsda_b200 status {status}: {msg}")

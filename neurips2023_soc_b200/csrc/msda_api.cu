@@ -1,0 +1,450 @@
+// msda_api.cu -- the C ABI of libmsda_b200.so (see include/msda_b200.h) and the host-side
+// dispatch onto the sm_100a kernels.  No torch / ATen types anywhere: plain pointers,
+// sizes, dtype enums and a cudaStream_t.
+//
+// Host logic mirrors ms_deform_attn_cuda_forward / ms_deform_attn_cuda_backward
+// (/root/reference/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80, :83-153): argument
+// validation, the im2col_step divisibility rule (:50-52), one launch sequence per call on
+// the caller's stream.  Unlike the reference (cuh:948-952) launch errors are returned.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+
+#include "../../include/msda_b200.h"
+#include "msda_backward.cuh"
+#include "msda_forward.cuh"
+
+namespace {
+
+using namespace msda;
+
+thread_local std::string g_error;
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define MSDA_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(MSDA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+#define MSDA_LAUNCHED(name)                                                               \
+    do {                                                                                  \
+        ++g_launches;                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                              \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(MSDA_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+size_t dtype_size(int dt) {
+    switch (dt) {
+        case MSDA_F32: return 4;
+        case MSDA_BF16: return 2;
+        case MSDA_F16: return 2;
+        case MSDA_F64: return 8;
+        default: return 0;
+    }
+}
+
+int num_sms() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+template <typename K>
+int blocks_per_sm(K kernel, int threads) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
+int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int check_common(const void* value, const int64_t* shapes, const int64_t* lsi, const void* loc,
+                 const void* attn, int N, int S, int M, int D, int L, int Lq, int P, int vdt,
+                 int adt, int im2col_step) {
+    if (!value || !shapes || !lsi || !loc || !attn)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT,
+                    "non-positive size: N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d", N, S, M, D, L, Lq, P);
+    if (dtype_size(vdt) == 0 || dtype_size(adt) == 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "unknown dtype (value %d, aux %d)", vdt, adt);
+    if (adt != vdt && !(adt == MSDA_F32 && vdt != MSDA_F64))
+        return fail(MSDA_ERR_INVALID_ARGUMENT,
+                    "aux dtype must equal the value dtype or be fp32 (value %d, aux %d)", vdt, adt);
+    if (im2col_step <= 0)
+        return fail(MSDA_ERR_IM2COL_STEP, "im2col_step must be positive, got %d", im2col_step);
+    const int step = N < im2col_step ? N : im2col_step;
+    if (N % step != 0)  // ms_deform_attn_cuda.cu:52
+        return fail(MSDA_ERR_IM2COL_STEP, "batch(%d) must divide im2col_step(%d)", N, step);
+    if (L > kMaxLevels)
+        return fail(MSDA_ERR_UNSUPPORTED, "at most %d feature levels are supported, got %d", kMaxLevels, L);
+    if ((long long)S * M * D >= (1LL << 31) || (long long)Lq * M * D >= (1LL << 31))
+        return fail(MSDA_ERR_UNSUPPORTED, "one frame must hold fewer than 2^31 elements");
+    if ((long long)N * M * ((long long)Lq + S) >= (1LL << 31))
+        return fail(MSDA_ERR_UNSUPPORTED, "N*M*(Lq+S) must stay below 2^31");
+    return MSDA_OK;
+}
+
+int id_shift_for(int LP) {
+    int s = 0;
+    while ((1 << s) < LP) ++s;
+    return s;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// lanes per row of the tile kernels, 0 when the shape has to take the generic path
+int tile_group(int D, int vdt, unsigned flags) {
+    if (flags & MSDA_FLAG_GENERIC) return 0;
+    if (vdt == MSDA_F64) return 0;
+    const size_t row = (size_t)D * dtype_size(vdt);
+    if (row == 64) return 4;
+    if (row == 128) return 8;
+    if (row == 256) return 16;
+    return 0;
+}
+
+int rounds_for(int G, int Lq) {
+    const int NG = kThreads / G;
+    const int full = kTileQ / NG;
+    const int need = ceil_div(Lq, NG);
+    return need < full ? need : full;
+}
+
+template <typename K>
+int persistent_grid(K kernel, long long work_items) {
+    const long long cap = (long long)num_sms() * blocks_per_sm(kernel, kThreads);
+    long long g = work_items < cap ? work_items : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+template <typename T, typename TA, int G>
+int launch_fwd_tile(const Params& p, cudaStream_t st) {
+    const int rounds = rounds_for(G, p.Lq);
+    const int tile_q = (kThreads / G) * rounds;
+    auto k = msda_fwd_tile_kernel<T, TA, G>;
+    const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
+    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p, rounds);
+    MSDA_LAUNCHED("msda_fwd_tile_kernel");
+    return MSDA_OK;
+}
+
+template <typename T, typename TA>
+int launch_fwd_tile_g(const Params& p, int G, cudaStream_t st) {
+    switch (G) {
+        case 4: return launch_fwd_tile<T, TA, 4>(p, st);
+        case 8: return launch_fwd_tile<T, TA, 8>(p, st);
+        default: return launch_fwd_tile<T, TA, 16>(p, st);
+    }
+}
+
+template <typename T, typename TA, typename CT>
+int launch_fwd_generic(const Params& p, cudaStream_t st) {
+    auto k = msda_fwd_generic_kernel<T, TA, CT>;
+    const long long blocks = ceil_div((long long)p.N * p.Lq * p.M * p.D, kThreads);
+    const long long cap = (long long)num_sms() * 16;
+    k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_fwd_generic_kernel");
+    return MSDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+template <typename T, typename TA, int G>
+int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
+    const int rounds = rounds_for(G, p.Lq);
+    const int tile_q = (kThreads / G) * rounds;
+    const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;
+    if constexpr (std::is_same<T, float>::value) {
+        if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) {
+            auto ka = msda_bwd_sample_tile_kernel<T, TA, G, true>;
+            ka<<<persistent_grid(ka, tiles), kThreads, 0, st>>>(p, rounds);
+            MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<atomic>");
+            return MSDA_OK;
+        }
+    }
+    auto k = msda_bwd_sample_tile_kernel<T, TA, G, false>;
+    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p, rounds);
+    MSDA_LAUNCHED("msda_bwd_sample_tile_kernel");
+    return MSDA_OK;
+}
+
+template <typename T, typename TA>
+int launch_bwd_sample_tile_g(const Params& p, int G, cudaStream_t st) {
+    switch (G) {
+        case 4: return launch_bwd_sample_tile<T, TA, 4>(p, st);
+        case 8: return launch_bwd_sample_tile<T, TA, 8>(p, st);
+        default: return launch_bwd_sample_tile<T, TA, 16>(p, st);
+    }
+}
+
+template <typename T, typename TA, typename CT>
+int launch_bwd_sample_generic(const Params& p, cudaStream_t st) {
+    auto k = msda_bwd_sample_generic_kernel<T, TA, CT>;
+    const long long blocks = ceil_div((long long)p.N * p.Lq * p.M, kThreads / 32);
+    const long long cap = (long long)num_sms() * 8;
+    k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bwd_sample_generic_kernel");
+    return MSDA_OK;
+}
+
+template <typename TA, typename CT>
+int launch_binning(const Params& p, cudaStream_t st) {
+    const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
+    const long long eb = ceil_div(samples, kThreads);
+    const long long cap = (long long)num_sms() * 16;
+    const int egrid = (int)(eb < cap ? eb : cap);
+    msda_bin_count_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bin_count_kernel");
+    msda_bin_scan_kernel<<<p.N * p.M, 1024, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bin_scan_kernel");
+    msda_bin_fill_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bin_fill_kernel");
+    const long long bins = (long long)p.N * p.M * p.sb_max;
+    const long long sb = ceil_div(bins, kThreads / 8);
+    const long long scap = (long long)num_sms() * 8;
+    msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bin_sort_small_kernel");
+    msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_bin_sort_big_kernel");
+    return MSDA_OK;
+}
+
+template <typename T, int G>
+int launch_grad_value_tile(const Params& p, cudaStream_t st) {
+    auto k = msda_grad_value_tile_kernel<T, G>;
+    const long long tiles = (long long)p.N * p.M * ceil_div(p.S, kThreads / G);
+    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_grad_value_tile_kernel");
+    return MSDA_OK;
+}
+
+template <typename T>
+int launch_grad_value_tile_g(const Params& p, int G, cudaStream_t st) {
+    switch (G) {
+        case 4: return launch_grad_value_tile<T, 4>(p, st);
+        case 8: return launch_grad_value_tile<T, 8>(p, st);
+        default: return launch_grad_value_tile<T, 16>(p, st);
+    }
+}
+
+template <typename T, typename CT>
+int launch_grad_value_generic(const Params& p, cudaStream_t st) {
+    auto k = msda_grad_value_generic_kernel<T, CT>;
+    const long long blocks = ceil_div((long long)p.N * p.S * p.M, kThreads / 32);
+    const long long cap = (long long)num_sms() * 8;
+    k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_grad_value_generic_kernel");
+    return MSDA_OK;
+}
+
+// workspace layout (bytes, every region 256-byte aligned)
+struct WsLayout {
+    size_t bin_off, big, pos, entries, total;
+    int sb_max, big_cap;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
+    WsLayout w;
+    const size_t samples = (size_t)N * Lq * M * L * P;
+    w.sb_max = 2 * S + 2 * L;  // sum (H+1)(W+1) = S + sum H + sum W + L <= 2S + 2L
+    w.big_cap = (int)(samples / (kBigBin + 1) + 1);
+    const size_t entry = vdt == MSDA_F64 ? sizeof(Entry<double>) : sizeof(Entry<float>);
+    w.bin_off = 0;
+    // the big-bin counter sits right behind the bin table so one memset clears both
+    w.big = (size_t)N * M * (w.sb_max + 1) * sizeof(uint32_t);
+    w.pos = align256(w.big + (1 + 2 * (size_t)w.big_cap) * sizeof(uint32_t));
+    w.entries = align256(w.pos + samples * sizeof(uint32_t));
+    w.total = align256(w.entries + samples * entry);
+    return w;
+}
+
+template <typename T, typename TA, typename CT>
+int backward_typed(Params& p, int G, cudaStream_t st) {
+    int rc;
+    if (G) {
+        if constexpr (!std::is_same<T, double>::value) {
+            if ((rc = launch_bwd_sample_tile_g<T, TA>(p, G, st))) return rc;
+        }
+    } else {
+        if ((rc = launch_bwd_sample_generic<T, TA, CT>(p, st))) return rc;
+    }
+    if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) return MSDA_OK;
+    if ((rc = launch_binning<TA, CT>(p, st))) return rc;
+    if (G) {
+        if constexpr (!std::is_same<T, double>::value) return launch_grad_value_tile_g<T>(p, G, st);
+    }
+    return launch_grad_value_generic<T, CT>(p, st);
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+int msda_version(void) { return MSDA_VERSION; }
+
+const char* msda_last_error(void) { return g_error.c_str(); }
+
+int msda_last_launch_count(void) { return g_launches; }
+
+int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                    const void* sampling_loc, const void* attn_weight, void* output, int N, int S, int M,
+                    int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
+                    void* cuda_stream, unsigned flags) {
+    g_launches = 0;
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
+                          Lq, P, value_dtype, aux_dtype, im2col_step);
+    if (rc) return rc;
+    if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "null output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
+    p.loc = sampling_loc; p.attn = attn_weight; p.out = output;
+    p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = L * P;
+    p.id_shift = id_shift_for(p.LP);
+    p.flags = flags;
+
+    int G = tile_group(D, value_dtype, flags);
+    if (G && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight))) G = 0;
+
+    const bool aux32 = aux_dtype == MSDA_F32;
+    switch (value_dtype) {
+        case MSDA_F32:
+            return G ? launch_fwd_tile_g<float, float>(p, G, st) : launch_fwd_generic<float, float, float>(p, st);
+        case MSDA_BF16:
+            if (aux32)
+                return G ? launch_fwd_tile_g<__nv_bfloat16, float>(p, G, st)
+                         : launch_fwd_generic<__nv_bfloat16, float, float>(p, st);
+            return G ? launch_fwd_tile_g<__nv_bfloat16, __nv_bfloat16>(p, G, st)
+                     : launch_fwd_generic<__nv_bfloat16, __nv_bfloat16, float>(p, st);
+        case MSDA_F16:
+            if (aux32)
+                return G ? launch_fwd_tile_g<__half, float>(p, G, st) : launch_fwd_generic<__half, float, float>(p, st);
+            return G ? launch_fwd_tile_g<__half, __half>(p, G, st) : launch_fwd_generic<__half, __half, float>(p, st);
+        default:
+            return launch_fwd_generic<double, double, double>(p, st);
+    }
+}
+
+int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight, void* output, int N, int S, int M, int D,
+                 int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream) {
+    return msda_forward_ex(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, N, S, M,
+                           D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, 0u);
+}
+
+size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                                     int aux_dtype) {
+    (void)D; (void)aux_dtype;
+    if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || Lq <= 0 || P <= 0) return 0;
+    return ws_layout(N, S, M, L, Lq, P, value_dtype).total;
+}
+
+int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                     const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                     size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                     int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
+    g_launches = 0;
+    int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
+                          Lq, P, value_dtype, aux_dtype, im2col_step);
+    if (rc) return rc;
+    if (!grad_output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null gradient pointer");
+    if ((flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) &&
+        !(value_dtype == MSDA_F32 && tile_group(D, value_dtype, flags)))
+        return fail(MSDA_ERR_UNSUPPORTED, "the atomic A/B arm exists for fp32 tile shapes only");
+    const int LP = L * P;
+    const int shift = id_shift_for(LP);
+    if (((long long)Lq << shift) >= (1LL << 31))
+        return fail(MSDA_ERR_UNSUPPORTED, "Lq * next_pow2(L*P) must stay below 2^31");
+    const WsLayout w = ws_layout(N, S, M, L, Lq, P, value_dtype);
+    const bool need_ws = !(flags & MSDA_FLAG_ATOMIC_GRAD_VALUE);
+    if (need_ws && (!workspace || workspace_bytes < w.total))
+        return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, got %zu", w.total,
+                    workspace ? workspace_bytes : (size_t)0);
+    if (need_ws && !aligned16(workspace))
+        return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
+    p.loc = sampling_loc; p.attn = attn_weight; p.grad_out = grad_output;
+    p.grad_value = grad_value; p.grad_loc = grad_sampling_loc; p.grad_attn = grad_attn_weight;
+    p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = LP;
+    p.id_shift = shift;
+    p.sb_max = w.sb_max; p.big_cap = w.big_cap;
+    p.flags = flags;
+    if (need_ws) {
+        char* base = static_cast<char*>(workspace);
+        p.bin_off = reinterpret_cast<uint32_t*>(base + w.bin_off);
+        p.big_bins = reinterpret_cast<uint32_t*>(base + w.big);
+        p.pos = reinterpret_cast<uint32_t*>(base + w.pos);
+        p.entries = base + w.entries;
+        MSDA_CUDA(cudaMemsetAsync(base + w.bin_off, 0, w.big + sizeof(uint32_t), st));
+        ++g_launches;
+    } else {
+        MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)N * S * M * D * dtype_size(value_dtype), st));
+        ++g_launches;
+    }
+
+    int G = tile_group(D, value_dtype, flags);
+    if (G && !(aligned16(value) && aligned16(grad_output) && aligned16(grad_value) && aligned16(sampling_loc) &&
+               aligned16(attn_weight) && aligned16(grad_sampling_loc) && aligned16(grad_attn_weight)))
+        G = 0;
+
+    const bool aux32 = aux_dtype == MSDA_F32;
+    switch (value_dtype) {
+        case MSDA_F32: return backward_typed<float, float, float>(p, G, st);
+        case MSDA_BF16:
+            return aux32 ? backward_typed<__nv_bfloat16, float, float>(p, G, st)
+                         : backward_typed<__nv_bfloat16, __nv_bfloat16, float>(p, G, st);
+        case MSDA_F16:
+            return aux32 ? backward_typed<__half, float, float>(p, G, st)
+                         : backward_typed<__half, __half, float>(p, G, st);
+        default: return backward_typed<double, double, double>(p, 0, st);
+    }
+}
+
+int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const void* sampling_loc, const void* attn_weight, const void* grad_output, void* grad_value,
+                  void* grad_sampling_loc, void* grad_attn_weight, void* workspace, size_t workspace_bytes, int N,
+                  int S, int M, int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
+                  void* cuda_stream) {
+    return msda_backward_ex(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes, N, S, M,
+                            D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, 0u);
+}
+
+}  // extern "C"

@@ -1,0 +1,288 @@
+// msda_common.cuh -- shared device-side definitions for the sm_100a MSDeformAttn kernels.
+//
+// Semantics implemented here are those of the reference op
+// (/root/reference/models/ops/src/cuda/ms_deform_im2col_cuda.cuh):
+//   sample position   h_im = loc_y*H - 0.5, w_im = loc_x*W - 0.5            (:285-286)
+//   accept            -1 < h_im < H  and  -1 < w_im < W                       (:288)
+//   corners           (h_lo,w_lo) (h_lo,w_hi) (h_hi,w_lo) (h_hi,w_hi), each dropped
+//                     on its own when outside [0,H-1]x[0,W-1]                 (:56-79)
+//   value row         value[n][level_start + h*W + w][m][0..D)                (:47-53,277)
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msda {
+
+constexpr int kMaxLevels = 16;   // levels held in shared memory per CTA
+constexpr int kThreads = 256;    // CTA size of the tile kernels
+constexpr int kSC = 16;          // samples staged per chunk (L*P = 16 in every SOC config)
+constexpr int kDescStride = kSC + 1;  // 16 B slots per query in the descriptor arrays (+1: bank skew)
+constexpr int kTileW = 16;       // pyramid query tile: kTileH x kTileW pixels of one level
+constexpr int kTileH = 8;
+constexpr int kTileQ = kTileW * kTileH;
+
+// Everything a kernel needs; passed by value.
+struct Params {
+    const void* value;
+    const int64_t* shapes;   // [L][2] (H, W), device
+    const int64_t* lsi;      // [L], device
+    const void* loc;         // [N][Lq][M][L][P][2]
+    const void* attn;        // [N][Lq][M][L][P]
+    const void* grad_out;    // [N][Lq][M*D]           (backward)
+    void* out;               // [N][Lq][M*D]           (forward)
+    void* grad_value;        // [N][S][M][D]
+    void* grad_loc;
+    void* grad_attn;
+    // backward workspace (see msda_backward.cuh)
+    uint32_t* bin_off;       // [N*M][sb_max + 1]  counts, then exclusive offsets
+    uint32_t* pos;           // [N*Lq*M*L*P]       slot of each sample inside its bin
+    void* entries;           // [N*M][Lq*L*P]      per-bin contribution lists
+    uint32_t* big_bins;      // [0] = count, then (nm, bin) pairs of bins with > 32 entries
+    int N, S, M, D, L, Lq, P;
+    int LP;                  // L*P
+    int id_shift;            // entry id = (q << id_shift) | s,  1<<id_shift >= LP
+    int sb_max;              // 2*S + 2*L: bound on sum_l (H_l+1)(W_l+1)
+    int big_cap;             // capacity of big_bins in pairs
+    unsigned flags;
+};
+
+struct Level {
+    int H, W;
+    int start;      // level_start_index[l]
+    int bin_start;  // sum_{l'<l} (H+1)(W+1)
+};
+
+// ---------------------------------------------------------------------------------------
+// element types
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kVec = 4;  // elements per 128-bit access
+    __device__ static float to_f(float v) { return v; }
+    __device__ static float from_f(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kVec = 8;
+    __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Elem<__half> {
+    static constexpr int kVec = 8;
+    __device__ static float to_f(__half v) { return __half2float(v); }
+    __device__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Elem<double> {
+    static constexpr int kVec = 2;
+    __device__ static double to_f(double v) { return v; }
+    __device__ static double from_f(double v) { return v; }
+};
+
+// 128-bit row fragment load -> fp32 registers (read-only path)
+__device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void load_vec(const __half* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void store_vec(__half* p, const float (&v)[8]) {
+    uint4 t;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = t;
+}
+
+// sampling location (x, y) and attention weight loads in the aux dtype
+template <typename CT> struct XY { CT x, y; };
+__device__ __forceinline__ XY<float> load_xy(const float* p) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    return {t.x, t.y};
+}
+__device__ __forceinline__ XY<float> load_xy(const __nv_bfloat16* p) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return {__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u)};
+}
+__device__ __forceinline__ XY<float> load_xy(const __half* p) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
+    return {f.x, f.y};
+}
+__device__ __forceinline__ XY<double> load_xy(const double* p) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    return {t.x, t.y};
+}
+
+// ---------------------------------------------------------------------------------------
+// geometry of one sample
+template <typename CT> struct Sample {
+    bool ok;
+    int h_lo, w_lo;
+    CT lh, lw;
+};
+
+__device__ __forceinline__ Sample<float> locate(float x, float y, int H, int W) {
+    Sample<float> s;
+    const float h_im = fmaf(y, (float)H, -0.5f);   // one rounding, as nvcc contracts :285-286
+    const float w_im = fmaf(x, (float)W, -0.5f);
+    s.ok = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+    const float hf = floorf(h_im), wf = floorf(w_im);
+    s.h_lo = (int)hf; s.w_lo = (int)wf;
+    s.lh = h_im - hf; s.lw = w_im - wf;
+    return s;
+}
+__device__ __forceinline__ Sample<double> locate(double x, double y, int H, int W) {
+    Sample<double> s;
+    const double h_im = fma(y, (double)H, -0.5);
+    const double w_im = fma(x, (double)W, -0.5);
+    s.ok = h_im > -1.0 && w_im > -1.0 && h_im < (double)H && w_im < (double)W;
+    const double hf = floor(h_im), wf = floor(w_im);
+    s.h_lo = (int)hf; s.w_lo = (int)wf;
+    s.lh = h_im - hf; s.lw = w_im - wf;
+    return s;
+}
+
+// Pixel index (inside the frame, i.e. level_start + h*W + w) of the four corners,
+// -1 for a corner outside the map.
+template <typename CT>
+__device__ __forceinline__ void corner_pixels(const Sample<CT>& s, const Level& lv, int (&pix)[4]) {
+    const int h_hi = s.h_lo + 1, w_hi = s.w_lo + 1;
+    const bool h0 = s.h_lo >= 0, w0 = s.w_lo >= 0, h1 = h_hi <= lv.H - 1, w1 = w_hi <= lv.W - 1;
+    const int base = lv.start + s.h_lo * lv.W + s.w_lo;
+    pix[0] = (h0 && w0) ? base : -1;
+    pix[1] = (h0 && w1) ? base + 1 : -1;
+    pix[2] = (h1 && w0) ? base + lv.W : -1;
+    pix[3] = (h1 && w1) ? base + lv.W + 1 : -1;
+}
+
+// Read the level table into shared memory (threads 0..L-1) and prefix the bin starts.
+// Returns sum_l (H+1)(W+1) through sb and sum_l H*W through sq.
+__device__ __forceinline__ void load_levels(const Params& p, Level* lv, int* sb, int* sq) {
+    if (threadIdx.x < p.L) {
+        const int l = threadIdx.x;
+        lv[l].H = (int)p.shapes[2 * l];
+        lv[l].W = (int)p.shapes[2 * l + 1];
+        lv[l].start = (int)p.lsi[l];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = 0, q = 0;
+        for (int l = 0; l < p.L; ++l) {
+            lv[l].bin_start = b;
+            b += (lv[l].H + 1) * (lv[l].W + 1);
+            q += lv[l].H * lv[l].W;
+        }
+        *sb = b;
+        *sq = q;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Query tiles.  A tile is a set of up to kTileQ queries of one (frame, head) handled by
+// one CTA pass.  When the queries are the pyramid's own pixels (encoder self-attention:
+// Lq == sum_l H_l*W_l, /root/reference/models/deformable_transformer.py:273-285) a tile
+// is a kTileH x kTileW pixel block of one level, so that the samples of the tile's
+// queries fall into a compact window of every level and hit in L1.  Otherwise a tile
+// is kTileQ consecutive queries.  The choice only affects locality, never results.
+struct TileMap {
+    int pyramid;          // 1: 2-D tiles per level, 0: linear
+    int qtiles;           // tiles per (frame, head)
+    int lvl_tile_start[kMaxLevels + 1];  // pyramid: prefix of tiles per level
+    int lvl_q_start[kMaxLevels];         // pyramid: first query index of each level
+};
+
+__device__ __forceinline__ void build_tile_map(const Params& p, const Level* lv, int sq, int tile_q, TileMap* tm) {
+    if (threadIdx.x == 0) {
+        const bool pyr = (sq == p.Lq) && !(p.flags & 1u) && tile_q == kTileQ;
+        tm->pyramid = pyr;
+        if (pyr) {
+            int t = 0, q = 0;
+            for (int l = 0; l < p.L; ++l) {
+                tm->lvl_tile_start[l] = t;
+                tm->lvl_q_start[l] = q;
+                t += ((lv[l].H + kTileH - 1) / kTileH) * ((lv[l].W + kTileW - 1) / kTileW);
+                q += lv[l].H * lv[l].W;
+            }
+            tm->lvl_tile_start[p.L] = t;
+            tm->qtiles = t;
+        } else {
+            tm->qtiles = (p.Lq + tile_q - 1) / tile_q;
+        }
+    }
+    __syncthreads();
+}
+
+struct Tile {
+    int n, m;
+    int q0;        // linear: first query
+    int lvl, y0, x0, Wq, Hq, qbase;  // pyramid: level, tile origin, level dims, first query of level
+};
+
+__device__ __forceinline__ Tile decode_tile(const Params& p, const Level* lv, const TileMap* tm, int t, int tile_q) {
+    Tile tl;
+    const int per_frame = tm->qtiles * p.M;
+    tl.n = t / per_frame;
+    const int r = t - tl.n * per_frame;
+    const int qt = r / p.M;
+    tl.m = r - qt * p.M;
+    tl.q0 = qt * tile_q;
+    tl.lvl = 0; tl.y0 = tl.x0 = 0; tl.Wq = tl.Hq = 1; tl.qbase = 0;
+    if (tm->pyramid) {
+        int l = 0;
+        while (l + 1 < p.L && qt >= tm->lvl_tile_start[l + 1]) ++l;
+        const int k = qt - tm->lvl_tile_start[l];
+        const int tw = (lv[l].W + kTileW - 1) / kTileW;
+        tl.lvl = l;
+        tl.y0 = (k / tw) * kTileH;
+        tl.x0 = (k % tw) * kTileW;
+        tl.Wq = lv[l].W; tl.Hq = lv[l].H;
+        tl.qbase = tm->lvl_q_start[l];
+    }
+    return tl;
+}
+
+// Query index of slot `idx` (0..tile_q) of a tile, or -1 when the slot is empty.
+__device__ __forceinline__ int tile_query(const Params& p, const TileMap* tm, const Tile& tl, int idx) {
+    if (tm->pyramid) {
+        const int y = tl.y0 + idx / kTileW, x = tl.x0 + idx % kTileW;
+        return (y < tl.Hq && x < tl.Wq) ? tl.qbase + y * tl.Wq + x : -1;
+    }
+    const int q = tl.q0 + idx;
+    return q < p.Lq ? q : -1;
+}
+
+}  // namespace msda

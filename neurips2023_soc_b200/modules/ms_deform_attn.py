@@ -1,0 +1,105 @@
+"""``MSDeformAttn`` -- the module API of the reference
+(/root/reference/models/ops/modules/ms_deform_attn.py:31-117), on the B200 kernels.
+
+Kept identical so that /root/reference/models/deformable_transformer.py runs unchanged
+and reference checkpoints load:
+  * constructor ``MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4)`` (:32),
+    attributes ``im2col_step=64`` (:49), ``d_model/n_levels/n_heads/n_points``;
+  * parameters ``sampling_offsets``, ``attention_weights``, ``value_proj``, ``output_proj``
+    (``nn.Linear`` each, :56-59) -> state-dict keys unchanged;
+  * ``_reset_parameters()`` (:63-77, called from outside at
+    /root/reference/models/deformable_transformer.py:68-70): zero offset weights, offset
+    bias = head m's compass direction scaled to unit max-norm times (p+1), zero attention
+    weights/bias, Xavier value/output projections with zero bias;
+  * ``forward(query, reference_points, input_flatten, input_spatial_shapes,
+    input_level_start_index, input_padding_mask=None)`` returning the 3-tuple
+    ``(output, sampling_locations, attention_weights)`` (:117, SOC's change to the
+    upstream Deformable-DETR module).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..functions import MSDeformAttnFunction
+
+
+def _power_of_two(n: int) -> bool:
+    if not isinstance(n, int) or n < 0:
+        raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4):
+        super().__init__()
+        if d_model % n_heads:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        if not _power_of_two(d_model // n_heads):
+            warnings.warn("MSDeformAttn: a per-head dimension that is a power of 2 (16..64 for fp32, 32..128 "
+                          "for bf16) takes the 128-bit tile kernels; other sizes use the generic kernels.")
+        self.im2col_step = 64
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+
+        samples = n_heads * n_levels * n_points
+        self.sampling_offsets = nn.Linear(d_model, 2 * samples)
+        self.attention_weights = nn.Linear(d_model, samples)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self) -> None:
+        with torch.no_grad():
+            angle = torch.arange(self.n_heads, dtype=torch.float32) * (2.0 * math.pi / self.n_heads)
+            compass = torch.stack([angle.cos(), angle.sin()], dim=-1)
+            compass = compass / compass.abs().max(dim=-1, keepdim=True).values
+            radius = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+            bias = compass.view(self.n_heads, 1, 1, 2) * radius          # (M, 1, P, 2)
+            bias = bias.expand(self.n_heads, self.n_levels, self.n_points, 2).reshape(-1)
+            self.sampling_offsets.weight.zero_()
+            self.sampling_offsets.bias = nn.Parameter(bias.clone())
+            self.attention_weights.weight.zero_()
+            self.attention_weights.bias.zero_()
+            nn.init.xavier_uniform_(self.value_proj.weight)
+            self.value_proj.bias.zero_()
+            nn.init.xavier_uniform_(self.output_proj.weight)
+            self.output_proj.bias.zero_()
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None):
+        """query (N, Lq, C); reference_points (N, Lq, L, 2|4) in [0, 1]; input_flatten (N, S, C);
+        input_spatial_shapes (L, 2) as (H, W); input_level_start_index (L,);
+        input_padding_mask (N, S), True on padding.  -> (output (N, Lq, C), sampling_locations,
+        attention_weights)."""
+        N, Lq, _ = query.shape
+        S = input_flatten.shape[1]
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == S
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], float(0))
+        value = value.view(N, S, M, self.d_model // M)
+
+        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+
+        box = reference_points.shape[-1]
+        if box == 2:
+            # offsets are in pixels of each level: divide by (W_l, H_l)
+            wh = input_spatial_shapes.flip(-1)
+            sampling_locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif box == 4:
+            # offsets are fractions of half the reference box, spread over the P points
+            sampling_locations = (reference_points[:, :, None, :, None, :2]
+                                  + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {box} instead.")
+
+        output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                            sampling_locations, weights, self.im2col_step)
+        return self.output_proj(output), sampling_locations, weights

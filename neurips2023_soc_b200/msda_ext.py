@@ -1,0 +1,115 @@
+"""Host side of the operator boundary: the two functions the reference binds from its
+compiled extension (/root/reference/models/ops/src/vision.cpp:13-16), with the same
+names, argument order and error behaviour, routed to libmsda_b200.so through ctypes.
+
+    ms_deform_attn_forward(value, spatial_shapes, level_start_index,
+                           sampling_loc, attn_weight, im2col_step) -> Tensor (N, Lq, M*D)
+    ms_deform_attn_backward(value, spatial_shapes, level_start_index,
+                            sampling_loc, attn_weight, grad_output, im2col_step)
+                           -> [grad_value, grad_sampling_loc, grad_attn_weight]
+
+Host logic mirrored from ms_deform_attn_cuda_forward / _backward
+(/root/reference/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80, :83-153):
+contiguity and device checks (:28-38, :93-105) raise RuntimeError, CPU tensors raise
+"Not implemented on the CPU" (/root/reference/models/ops/src/ms_deform_attn.h:38,60), the
+callee allocates the results with the dtype/device of ``value`` (:54, :121-123) and the
+work is queued on the current CUDA stream (:65, :135) without synchronising.
+
+torch is used for device memory and the stream handle only.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _lib
+
+_DTYPE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16, torch.float64: _lib.F64}
+
+#: bench/diagnostic switch: flags forwarded to msda_*_ex (0 in production)
+DEFAULT_FLAGS = 0
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_inputs(named):
+    for name, t in named:
+        _require(isinstance(t, torch.Tensor), f"{name} must be a tensor")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    if not named[0][1].is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    dev = named[0][1].device
+    for name, t in named:
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.device == dev, f"{name} must be on {dev}, found {t.device}")
+
+
+def _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    _require(value.dim() == 4, "value must be (N, S, M, D)")
+    _require(sampling_loc.dim() == 6 and sampling_loc.shape[-1] == 2, "sampling_loc must be (N, Lq, M, L, P, 2)")
+    _require(attn_weight.dim() == 5, "attn_weight must be (N, Lq, M, L, P)")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes and level_start_index must be int64")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    _, Lq, M2, L2, P, _ = sampling_loc.shape
+    _require(spatial_shapes.dim() == 2 and spatial_shapes.shape[1] == 2, "spatial_shapes must be (L, 2)")
+    _require(level_start_index.numel() == L, "level_start_index must have L entries")
+    _require(sampling_loc.shape[0] == N and M2 == M and L2 == L, "sampling_loc does not match value / spatial_shapes")
+    _require(tuple(attn_weight.shape) == (N, Lq, M, L, P), "attn_weight does not match sampling_loc")
+    _require(value.dtype in _DTYPE, f"unsupported value dtype {value.dtype}")
+    _require(sampling_loc.dtype == attn_weight.dtype, "sampling_loc and attn_weight must share a dtype")
+    _require(sampling_loc.dtype == value.dtype or (sampling_loc.dtype == torch.float32 and value.dtype != torch.float64),
+             f"sampling_loc/attn_weight must be {value.dtype} or float32, found {sampling_loc.dtype}")
+    return (N, S, M, D, L, Lq, P), _DTYPE[value.dtype], _DTYPE[sampling_loc.dtype]
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                           im2col_step: int, flags: int | None = None) -> torch.Tensor:
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
+    dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    N, S, M, D, L, Lq, P = dims
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.msda_forward_ex(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+            *dims, vdt, adt, int(im2col_step), stream, DEFAULT_FLAGS if flags is None else flags))
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step: int, flags: int | None = None) -> List[torch.Tensor]:
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    N, S, M, D, L, Lq, P = dims
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == N * Lq * M * D,
+             "grad_output must be (N, Lq, M*D) in the dtype of value")
+    lib = _lib.load()
+    flags = DEFAULT_FLAGS if flags is None else flags
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_loc = torch.empty_like(sampling_loc)
+        grad_attn = torch.empty_like(attn_weight)
+        ws_bytes = 0 if flags & _lib.FLAG_ATOMIC_GRAD_VALUE else int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.msda_backward_ex(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+            ws.data_ptr(), ws_bytes, *dims, vdt, adt, int(im2col_step), stream, flags))
+        # `ws` may be released to the caching allocator here: reuse is ordered on this stream
+    return [grad_value, grad_loc, grad_attn]
+
+
+def last_launch_count() -> int:
+    return int(_lib.load().msda_last_launch_count())

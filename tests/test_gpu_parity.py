@@ -1,0 +1,274 @@
+"""Parity of the sm_100a kernels (through the C ABI) with the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): max-abs error <= 1e-5 for fp32 and <= 2e-2 for bf16,
+taken relative to max(1, max|reference|) so that gradients that sum thousands of terms are
+judged on the same footing as O(1) outputs.  bf16 cases compare against the oracle evaluated in
+fp64 on the bf16-rounded inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from neurips2023_soc_b200 import MSDeformAttnFunction, _lib, msda_ext
+from neurips2023_soc_b200.synthetic import A2D_PYRAMID, make_inputs
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL = {torch.float64: 1e-11, torch.float32: 1e-5, torch.bfloat16: 2e-2, torch.float16: 2e-3}
+
+
+def rel_err(a, ref, keep=None):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    err = np.abs(a.reshape(ref.shape) - ref)
+    if keep is not None:
+        err = err * keep
+    return float(err.max()) / max(1.0, float(np.abs(ref).max()))
+
+
+def off_lattice(loc, shapes, eps=1e-3):
+    loc = np.asarray(loc, np.float64)
+    wh = np.asarray(shapes)[:, ::-1].astype(np.float64).reshape(1, 1, 1, -1, 1, 2)
+    px = loc * wh - 0.5
+    ok = (np.abs(px - np.round(px)) > eps).all(-1, keepdims=True)
+    return np.broadcast_to(ok, loc.shape).astype(np.float64)
+
+
+def run_op(value, shapes, lsi, loc, attn, grad_out, vdt, adt, flags=0):
+    """forward + backward through the extension-level API on the GPU."""
+    v = value.to(DEV, vdt).contiguous()
+    lo, at = loc.to(DEV, adt).contiguous(), attn.to(DEV, adt).contiguous()
+    sh, ls = shapes.to(DEV), lsi.to(DEV)
+    go = grad_out.to(DEV, vdt).contiguous()
+    out = msda_ext.ms_deform_attn_forward(v, sh, ls, lo, at, 64, flags=flags)
+    gv, gl, ga = msda_ext.ms_deform_attn_backward(v, sh, ls, lo, at, go, 64, flags=flags)
+    torch.cuda.synchronize()
+    return out, gv, gl, ga, (v, lo, at, go)
+
+
+def oracle_f64(v, shapes, lsi, lo, at, go):
+    args = [t.detach().double().cpu().numpy() for t in (v, lo, at, go)]
+    out = O.forward_c(args[0], shapes.numpy(), lsi.numpy(), args[1], args[2])
+    gv, gl, ga = O.backward_c(args[0], shapes.numpy(), lsi.numpy(), args[1], args[2], args[3])
+    return out, gv, gl, ga
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.float64, torch.float64)])
+def test_golden_vectors(name, vdt, adt):
+    g = load_golden(name)
+    t = {k: torch.from_numpy(g[k]) for k in ("value", "loc", "attn", "grad_out", "shapes", "lsi")}
+    out, gv, gl, ga, _ = run_op(t["value"], t["shapes"], t["lsi"], t["loc"], t["attn"], t["grad_out"], vdt, adt)
+    tol = TOL[vdt]
+    keep = off_lattice(g["loc"], g["shapes"], 1e-3 if vdt == torch.float32 else 0.0)
+    if vdt == torch.float64:  # only the accept-boundary kink differs from autograd (see oracle header)
+        wh = g["shapes"][:, ::-1].astype(np.float64).reshape(1, 1, 1, -1, 1, 2)
+        px = g["loc"].astype(np.float64) * wh - 0.5
+        keep = np.broadcast_to((px != -1.0).all(-1, keepdims=True), px.shape).astype(np.float64)
+    assert rel_err(out, g["out"]) <= tol
+    assert rel_err(gv, g["grad_value"]) <= tol
+    assert rel_err(ga, g["grad_attn"]) <= tol
+    assert rel_err(gl, g["grad_loc"], keep) <= 2 * tol
+
+
+@pytest.mark.parametrize("name", ["encoder_like", "decoder_like", "p8_l1", "channels_64", "out_of_range"])
+@pytest.mark.parametrize("vdt,adt", [(torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                      (torch.float16, torch.float32)])
+def test_golden_inputs_reduced_precision(name, vdt, adt):
+    g = load_golden(name)
+    t = {k: torch.from_numpy(g[k]) for k in ("value", "loc", "attn", "grad_out", "shapes", "lsi")}
+    out, gv, gl, ga, (v, lo, at, go) = run_op(t["value"], t["shapes"], t["lsi"], t["loc"], t["attn"],
+                                               t["grad_out"], vdt, adt)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, t["shapes"], t["lsi"], lo, at, go)
+    tol = TOL[vdt]
+    keep = off_lattice(lo.double().cpu().numpy(), g["shapes"], 2e-2 if adt != torch.float32 else 1e-3)
+    assert rel_err(out, r_out) <= tol
+    assert rel_err(gv, r_gv) <= tol
+    assert rel_err(ga, r_ga) <= tol
+    assert rel_err(gl, r_gl, keep) <= 2 * tol
+
+
+@pytest.mark.parametrize("dist", ["encoder", "uniform"])
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_config1_shape_vs_c_oracle(dist, vdt, adt):
+    """BASELINE config 1: one frame of the A2D pyramid, 5100 queries, 8 heads x 32, 4 levels x 4 points."""
+    x = make_inputs(N=1, dist=dist, seed=1)
+    out, gv, gl, ga, (v, lo, at, go) = run_op(x.value, x.spatial_shapes, x.level_start_index,
+                                               x.sampling_locations, x.attention_weights, x.grad_output, vdt, adt)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    tol = TOL[vdt]
+    keep = off_lattice(lo.double().cpu().numpy(), x.spatial_shapes.numpy(), 1e-3)
+    assert rel_err(out, r_out) <= tol
+    assert rel_err(gv, r_gv) <= tol
+    assert rel_err(ga, r_ga) <= tol
+    assert rel_err(gl, r_gl, keep) <= 2 * tol
+
+
+@pytest.mark.parametrize("kw", [dict(N=2, dist="decoder", Lq=20), dict(N=3, dist="decoder", Lq=5),
+                                dict(N=2, dist="uniform", Lq=300, P=8),
+                                dict(N=1, dist="encoder", shapes=[(9, 13), (5, 7)], M=4, D=16),
+                                dict(N=1, dist="encoder", shapes=[(9, 13), (5, 7)], M=2, D=64),
+                                dict(N=1, dist="uniform", shapes=[(7, 5)], M=3, D=20, Lq=33, P=3)])
+def test_shape_sweep_fp32(kw):
+    x = make_inputs(seed=5, **kw)
+    out, gv, gl, ga, (v, lo, at, go) = run_op(x.value, x.spatial_shapes, x.level_start_index,
+                                               x.sampling_locations, x.attention_weights, x.grad_output,
+                                               torch.float32, torch.float32)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    keep = off_lattice(lo.double().cpu().numpy(), x.spatial_shapes.numpy(), 1e-3)
+    assert rel_err(out, r_out) <= 1e-5
+    assert rel_err(gv, r_gv) <= 1e-5
+    assert rel_err(ga, r_ga) <= 1e-5
+    assert rel_err(gl, r_gl, keep) <= 2e-5
+
+
+def test_generic_and_tile_paths_agree():
+    x = make_inputs(N=2, dist="encoder", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], seed=2)
+    a = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+               x.grad_output, torch.float32, torch.float32)
+    b = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+               x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_GENERIC)
+    c = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+               x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_LINEAR_TILES)
+    for i in range(4):
+        assert rel_err(a[i], b[i].double().cpu().numpy()) <= 1e-5
+        assert torch.equal(a[i], c[i]), "query tiling must not change a single bit"
+
+
+def test_backward_is_bit_reproducible():
+    """The reference's fp32 atomicAdd scatter (cuh:125-152) is order-dependent; this one is not."""
+    x = make_inputs(N=2, dist="encoder", seed=3)
+    first = None
+    for _ in range(5):
+        r = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+                   x.grad_output, torch.float32, torch.float32)
+        if first is None:
+            first = r
+        else:
+            for i in range(4):
+                assert torch.equal(first[i], r[i])
+
+
+def test_atomic_arm_matches_deterministic_path():
+    x = make_inputs(N=1, dist="encoder", seed=4)
+    a = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+               x.grad_output, torch.float32, torch.float32)
+    b = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+               x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_ATOMIC_GRAD_VALUE)
+    for i in range(4):
+        assert rel_err(b[i], a[i].double().cpu().numpy()) <= 1e-5
+
+
+def test_many_samples_in_one_bin():
+    """All queries look at the same spot: one bin holds every sample of its level (exercises the
+    shared-memory and the in-place global sort of big bins)."""
+    x = make_inputs(N=1, dist="uniform", shapes=[(6, 10), (3, 5)], M=2, D=32, Lq=1500, seed=6)
+    loc = x.sampling_locations * 0.0 + torch.tensor([0.43, 0.57])
+    loc[:, :700] += 0.001 * torch.randn(1, 700, 2, 2, 4, 2, generator=torch.Generator().manual_seed(1))
+    res = [run_op(x.value, x.spatial_shapes, x.level_start_index, loc, x.attention_weights, x.grad_output,
+                  torch.float32, torch.float32) for _ in range(2)]
+    out, gv, gl, ga, (v, lo, at, go) = res[0]
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    assert rel_err(out, r_out) <= 1e-5
+    assert rel_err(gv, r_gv) <= 1e-5
+    assert rel_err(ga, r_ga) <= 1e-5
+    assert torch.equal(res[0][1], res[1][1])
+
+
+# ---------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_full_a2d_shape_properties(vdt, adt):
+    """BASELINE config 2 shape (16 frames x 5100 tokens).  Size-independent checks:
+    * value == 1 and every sample strictly inside the map  =>  output == sum of weights == 1;
+    * then sum over pixels of grad_value[n, :, m, c] == sum over queries of grad_output[n, :, m, c];
+    * linearity in value: f(2 v1 - v2) == 2 f(v1) - f(v2);
+    * frames are independent: frame 5 alone reproduces frame 5 of the batch bit for bit."""
+    x = make_inputs(N=16, dist="encoder", seed=7)
+    sh, ls = x.spatial_shapes.to(DEV), x.level_start_index.to(DEV)
+    wh = x.spatial_shapes.flip(-1).float().view(1, 1, 1, -1, 1, 2)
+    loc = ((x.sampling_locations * wh).clamp(min=0.75) - 0.0)
+    loc = torch.minimum(loc, wh - 0.75) / wh                     # corners all valid
+    loc, attn = loc.to(DEV, adt).contiguous(), x.attention_weights.to(DEV, adt).contiguous()
+    ones = torch.ones_like(x.value).to(DEV, vdt)
+    go = x.grad_output.to(DEV, vdt)
+    out = msda_ext.ms_deform_attn_forward(ones, sh, ls, loc, attn, 64)
+    tol = 1e-5 if vdt == torch.float32 else 1e-2
+    assert float((out.float() - 1).abs().max()) <= tol
+    gv, gl, ga = msda_ext.ms_deform_attn_backward(ones, sh, ls, loc, attn, go, 64)
+    lhs = gv.float().sum(1)                                      # (N, M, D)
+    rhs = go.float().view(16, -1, 8, 32).sum(1)
+    assert float((lhs - rhs).abs().max()) <= (1e-2 if vdt == torch.float32 else 1.0)
+    assert float(gl.float().abs().max()) <= (1e-3 if vdt == torch.float32 else 0.5)  # constant image: no slope
+
+    v1 = x.value.to(DEV, vdt)
+    v2 = torch.roll(x.value, 1, 1).to(DEV, vdt)
+    loc_r, attn_r = x.sampling_locations.to(DEV, adt), x.attention_weights.to(DEV, adt)
+    f1 = msda_ext.ms_deform_attn_forward(v1, sh, ls, loc_r, attn_r, 64).float()
+    f2 = msda_ext.ms_deform_attn_forward(v2, sh, ls, loc_r, attn_r, 64).float()
+    f3 = msda_ext.ms_deform_attn_forward((2 * v1.float() - v2.float()).to(vdt), sh, ls, loc_r, attn_r, 64).float()
+    assert float((f3 - (2 * f1 - f2)).abs().max()) <= (2e-5 if vdt == torch.float32 else 8e-2)
+
+    one = msda_ext.ms_deform_attn_forward(v1[5:6].contiguous(), sh, ls, loc_r[5:6].contiguous(),
+                                          attn_r[5:6].contiguous(), 64)
+    assert torch.equal(one[0], msda_ext.ms_deform_attn_forward(v1, sh, ls, loc_r, attn_r, 64)[5])
+    go1 = go[5:6].contiguous()
+    g_one = msda_ext.ms_deform_attn_backward(v1[5:6].contiguous(), sh, ls, loc_r[5:6].contiguous(),
+                                             attn_r[5:6].contiguous(), go1, 64)
+    g_all = msda_ext.ms_deform_attn_backward(v1, sh, ls, loc_r, attn_r, go, 64)
+    for a, b in zip(g_one, g_all):
+        assert torch.equal(a[0], b[5])
+
+
+def test_full_a2d_shape_vs_grid_sample_port_on_gpu():
+    """16 frames at once against the reference's own formulation (grid_sample) evaluated by torch
+    on the same GPU in fp32 -- the N = 16 counterpart of the fp64 CPU check above."""
+    x = make_inputs(N=16, dist="encoder", seed=8).to(DEV)
+    out = msda_ext.ms_deform_attn_forward(x.value, x.spatial_shapes, x.level_start_index,
+                                          x.sampling_locations, x.attention_weights, 64)
+    gv, gl, ga = msda_ext.ms_deform_attn_backward(x.value, x.spatial_shapes, x.level_start_index,
+                                                  x.sampling_locations, x.attention_weights, x.grad_output, 64)
+    ref = O.grid_sample_port_grads(x.value, x.spatial_shapes.cpu(), x.sampling_locations, x.attention_weights,
+                                   x.grad_output)
+    keep = off_lattice(x.sampling_locations.cpu().numpy(), x.spatial_shapes.cpu().numpy(), 1e-3)
+    assert rel_err(out, ref[0].double().cpu().numpy()) <= 1e-5
+    assert rel_err(gv, ref[1].double().cpu().numpy()) <= 2e-5     # torch's own scatter is fp32-atomic
+    assert rel_err(ga, ref[3].double().cpu().numpy()) <= 1e-5
+    assert rel_err(gl, ref[2].double().cpu().numpy(), keep) <= 5e-5
+
+
+# ---------------------------------------------------------------------------- autograd boundary
+def test_autograd_function_and_gradcheck():
+    """models/ops/test.py:63-78: fp64 gradcheck of the op for several channel counts."""
+    shapes = torch.tensor([(6, 4), (3, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.tensor([0, 24], dtype=torch.long, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    for D in (30, 32, 64, 71):
+        value = (torch.rand(1, 30, 2, D, generator=g) * 0.01).double().to(DEV).requires_grad_(True)
+        loc = torch.rand(1, 2, 2, 2, 2, 2, generator=g).double().to(DEV).requires_grad_(True)
+        attn = torch.rand(1, 2, 2, 2, 2, generator=g) + 1e-5
+        attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().to(DEV).requires_grad_(True)
+        assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+def test_error_behaviour():
+    x = make_inputs(N=3, dist="decoder", Lq=4, shapes=[(4, 4)], M=2, D=32, seed=9)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        msda_ext.ms_deform_attn_forward(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                        x.attention_weights, 64)
+    d = x.to(DEV)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        msda_ext.ms_deform_attn_forward(d.value.transpose(1, 2), d.spatial_shapes, d.level_start_index,
+                                        d.sampling_locations, d.attention_weights, 64)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):   # ms_deform_attn_cuda.cu:52
+        msda_ext.ms_deform_attn_forward(d.value, d.spatial_shapes, d.level_start_index, d.sampling_locations,
+                                        d.attention_weights, 2)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        msda_ext.ms_deform_attn_forward(d.value, x.spatial_shapes, d.level_start_index, d.sampling_locations,
+                                        d.attention_weights, 64)
+    out = msda_ext.ms_deform_attn_forward(d.value, d.spatial_shapes, d.level_start_index, d.sampling_locations,
+                                          d.attention_weights, 3)
+    assert out.shape == (3, 4, 64) and msda_ext.last_launch_count() == 1

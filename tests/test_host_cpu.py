@@ -1,0 +1,103 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol the header
+declares, argument validation runs before any CUDA call, and the Python mirror fails loudly
+instead of falling back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from neurips2023_soc_b200 import MSDeformAttn, MSDeformAttnFunction, _lib, build, msda_ext
+from neurips2023_soc_b200.synthetic import algorithmic_bytes, make_inputs, scaled_pyramid
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_library()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = (ROOT / "include" / "msda_b200.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|size_t|const char \*)\s*\*?\s*(msda_\w+)\s*\(", header, re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/msda_b200.h but not exported"
+    assert lib.msda_version() == int(re.search(r"#define MSDA_VERSION (\d+)", header).group(1))
+
+
+def test_validation_precedes_cuda(lib):
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)
+    assert lib.msda_forward(null, null, null, null, null, null, 1, 1, 1, 32, 1, 1, 1, 0, 0, 64, null) == 1
+    assert b"null" in lib.msda_last_error()
+    assert lib.msda_forward(one, one, one, one, one, one, 0, 1, 1, 32, 1, 1, 1, 0, 0, 64, null) == 1
+    assert lib.msda_forward(one, one, one, one, one, one, 3, 4, 1, 32, 1, 1, 1, 0, 0, 2, null) == 2
+    assert b"must divide im2col_step" in lib.msda_last_error()
+    assert lib.msda_forward(one, one, one, one, one, one, 2, 4, 1, 32, 1, 1, 1, 0, 1, 64, null) == 1  # aux bf16, value f32
+    assert lib.msda_forward(one, one, one, one, one, one, 2, 4, 1, 32, 17, 1, 1, 0, 0, 64, null) == 5  # > 16 levels
+    # backward without a workspace
+    assert lib.msda_backward(one, one, one, one, one, one, one, one, one, null, 0, 2, 4, 1, 32, 1, 1, 1, 0, 0, 64, null) == 3
+
+
+def test_workspace_size(lib):
+    small = lib.msda_backward_workspace_bytes(1, 5100, 8, 32, 4, 5100, 4, 0, 0)
+    big = lib.msda_backward_workspace_bytes(16, 5100, 8, 32, 4, 5100, 4, 0, 0)
+    assert 0 < small < big
+    samples = 16 * 5100 * 8 * 16
+    assert big >= samples * (16 + 4)                      # entries + slot per sample
+    assert big < samples * (16 + 4) + (64 << 20)          # plus the bin tables, nothing more
+    assert lib.msda_backward_workspace_bytes(0, 1, 1, 1, 1, 1, 1, 0, 0) == 0
+
+
+def test_no_cpu_fallback():
+    x = make_inputs(N=1, dist="decoder", Lq=3, shapes=[(4, 4)], M=2, D=32)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDeformAttnFunction.apply(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                   x.attention_weights, 64)
+    m = MSDeformAttn(d_model=64, n_levels=1, n_heads=2, n_points=2)
+    q = torch.randn(1, 3, 64)
+    ref = torch.rand(1, 3, 1, 2)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        m(q, ref, torch.randn(1, 16, 64), x.spatial_shapes, x.level_start_index)
+
+
+def test_missing_library_is_loud(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libmsda_b200.so")
+    with pytest.raises(_lib.MSDAError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_module_api_and_state_dict():
+    m = MSDeformAttn()
+    assert (m.im2col_step, m.d_model, m.n_levels, m.n_heads, m.n_points) == (64, 256, 4, 8, 4)
+    assert sorted(m.state_dict()) == sorted(
+        f"{n}.{p}" for n in ("sampling_offsets", "attention_weights", "value_proj", "output_proj")
+        for p in ("weight", "bias"))
+    assert m.sampling_offsets.weight.shape == (256, 256) and m.attention_weights.weight.shape == (128, 256)
+    b = m.sampling_offsets.bias.view(8, 4, 4, 2)
+    assert torch.allclose(b[0, :, :, 0], torch.tensor([1., 2., 3., 4.]).expand(4, 4))   # head 0 looks along +x
+    assert torch.allclose(b[2, :, 3], torch.tensor([0., 4.]).expand(4, 2), atol=1e-6)    # head 2 along +y
+    with pytest.raises(ValueError):
+        MSDeformAttn(d_model=250, n_heads=8)
+
+
+def test_synthetic_inputs():
+    x = make_inputs(N=2, dist="encoder")
+    assert x.value.shape == (2, 5100, 8, 32) and x.sampling_locations.shape == (2, 5100, 8, 4, 4, 2)
+    assert x.level_start_index.tolist() == [0, 3840, 4800, 5040]
+    assert torch.allclose(x.attention_weights.sum((-1, -2)), torch.ones(2, 5100, 8), atol=1e-5)
+    y = make_inputs(N=2, dist="encoder")
+    assert torch.equal(x.sampling_locations, y.sampling_locations)
+    u = make_inputs(N=1, dist="uniform", seed=1)
+    outside = ((u.sampling_locations < 0) | (u.sampling_locations > 1)).any(-1).float().mean()
+    assert 0.005 < float(outside) < 0.05
+    assert sum(h * w for h, w in scaled_pyramid(20000)) > 15000
+    fwd, bwd = algorithmic_bytes(16, 5100, 8, 32, 4, 5100, 4, 4, 4)
+    assert (fwd, bwd) == (81600 * 3584, 81600 * 6144)
+    fwd, bwd = algorithmic_bytes(16, 5100, 8, 32, 4, 5100, 4, 2, 4)
+    assert (fwd, bwd) == (81600 * 2560, 81600 * 4608)
