@@ -9,7 +9,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libmsda_b200.so"
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
-FLAG_LINEAR_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE = 1, 2, 4
+FLAG_LINEAR_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC8 = 1, 2, 4, 8
 
 EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",

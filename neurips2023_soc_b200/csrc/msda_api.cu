@@ -103,8 +103,8 @@ int check_common(const void* value, const int64_t* shapes, const int64_t* lsi, c
         return fail(MSDA_ERR_UNSUPPORTED, "at most %d feature levels are supported, got %d", kMaxLevels, L);
     if ((long long)S * M * D >= (1LL << 31) || (long long)Lq * M * D >= (1LL << 31))
         return fail(MSDA_ERR_UNSUPPORTED, "one frame must hold fewer than 2^31 elements");
-    if ((long long)N * M * ((long long)Lq + S) >= (1LL << 31))
-        return fail(MSDA_ERR_UNSUPPORTED, "N*M*(Lq+S) must stay below 2^31");
+    if ((long long)N * M * ((long long)L * Lq * P / 3 + 4LL * S + 4LL * L + 2) >= (1LL << 31))
+        return fail(MSDA_ERR_UNSUPPORTED, "N*M*(L*Lq*P/3 + 4S) must stay below 2^31");
     return MSDA_OK;
 }
 
@@ -116,15 +116,35 @@ int id_shift_for(int LP) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// lanes per row of the tile kernels, 0 when the shape has to take the generic path
-int tile_group(int D, int vdt, unsigned flags) {
-    if (flags & MSDA_FLAG_GENERIC) return 0;
-    if (vdt == MSDA_F64) return 0;
-    const size_t row = (size_t)D * dtype_size(vdt);
-    if (row == 64) return 4;
-    if (row == 128) return 8;
-    if (row == 256) return 16;
-    return 0;
+// ------------------------------------------------------------------------------------------
+// Which kernels a problem takes.  Tile kernels: fp32 rows of 64/128/256 B (D = 16/32/64),
+// bf16 rows of 64/128/256 B (D = 32/64/128), P in {4, 8}.  Everything else (fp16, fp64, odd
+// channel counts, other P) runs on the generic kernels.
+struct Plan {
+    bool tile;
+    int vec, g;        // sample kernels (forward, grad_loc/grad_attn)
+    int wvec, wg;      // grad_value walker
+};
+
+Plan make_plan(int D, int P, int vdt, unsigned flags) {
+    Plan pl{false, 0, 0, 0, 0};
+    if (flags & MSDA_FLAG_GENERIC) return pl;
+    if (P != 4 && P != 8) return pl;
+    if (vdt == MSDA_F32) {
+        if (D != 16 && D != 32 && D != 64) return pl;
+        pl = Plan{true, 4, D / 4, 4, D / 4};
+    } else if (vdt == MSDA_BF16) {
+        if (D == 32) {
+            // 64-byte rows: 8 lanes x 64 bit keep a row on as many lanes as an fp32 row;
+            // MSDA_FLAG_BF16_VEC8 selects 4 lanes x 128 bit instead (A/B switch)
+            pl = (flags & MSDA_FLAG_BF16_VEC8) ? Plan{true, 8, 4, 4, 8} : Plan{true, 4, 8, 4, 8};
+        } else if (D == 64) {
+            pl = Plan{true, 8, 8, 4, 16};
+        } else if (D == 128) {
+            pl = Plan{true, 8, 16, 8, 16};
+        }
+    }
+    return pl;
 }
 
 int rounds_for(int G, int Lq) {
@@ -135,32 +155,23 @@ int rounds_for(int G, int Lq) {
 }
 
 template <typename K>
-int persistent_grid(K kernel, long long work_items) {
-    const long long cap = (long long)num_sms() * blocks_per_sm(kernel, kThreads);
+int persistent_grid(K kernel, int threads, long long work_items) {
+    const long long cap = (long long)num_sms() * blocks_per_sm(kernel, threads);
     long long g = work_items < cap ? work_items : cap;
     return (int)(g < 1 ? 1 : g);
 }
 
 // ------------------------------------------------------------------------------------------
 // forward
-template <typename T, typename TA, int G>
+template <typename T, typename TA, int VEC, int G, int P>
 int launch_fwd_tile(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
-    auto k = msda_fwd_tile_kernel<T, TA, G>;
+    auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P>;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
-    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p, rounds);
+    k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     MSDA_LAUNCHED("msda_fwd_tile_kernel");
     return MSDA_OK;
-}
-
-template <typename T, typename TA>
-int launch_fwd_tile_g(const Params& p, int G, cudaStream_t st) {
-    switch (G) {
-        case 4: return launch_fwd_tile<T, TA, 4>(p, st);
-        case 8: return launch_fwd_tile<T, TA, 8>(p, st);
-        default: return launch_fwd_tile<T, TA, 16>(p, st);
-    }
 }
 
 template <typename T, typename TA, typename CT>
@@ -175,32 +186,23 @@ int launch_fwd_generic(const Params& p, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // backward
-template <typename T, typename TA, int G>
+template <typename T, typename TA, int VEC, int G, int P>
 int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;
     if constexpr (std::is_same<T, float>::value) {
         if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) {
-            auto ka = msda_bwd_sample_tile_kernel<T, TA, G, true>;
-            ka<<<persistent_grid(ka, tiles), kThreads, 0, st>>>(p, rounds);
+            auto ka = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, false, true>;
+            ka<<<persistent_grid(ka, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
             MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<atomic>");
             return MSDA_OK;
         }
     }
-    auto k = msda_bwd_sample_tile_kernel<T, TA, G, false>;
-    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p, rounds);
+    auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false>;
+    k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     MSDA_LAUNCHED("msda_bwd_sample_tile_kernel");
     return MSDA_OK;
-}
-
-template <typename T, typename TA>
-int launch_bwd_sample_tile_g(const Params& p, int G, cudaStream_t st) {
-    switch (G) {
-        case 4: return launch_bwd_sample_tile<T, TA, 4>(p, st);
-        case 8: return launch_bwd_sample_tile<T, TA, 8>(p, st);
-        default: return launch_bwd_sample_tile<T, TA, 16>(p, st);
-    }
 }
 
 template <typename T, typename TA, typename CT>
@@ -213,44 +215,45 @@ int launch_bwd_sample_generic(const Params& p, cudaStream_t st) {
     return MSDA_OK;
 }
 
-template <typename TA, typename CT>
-int launch_binning(const Params& p, cudaStream_t st) {
-    const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
-    const long long eb = ceil_div(samples, kThreads);
+int elementwise_grid(long long items) {
+    const long long eb = ceil_div(items, kThreads);
     const long long cap = (long long)num_sms() * 16;
-    const int egrid = (int)(eb < cap ? eb : cap);
-    msda_bin_count_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
-    MSDA_LAUNCHED("msda_bin_count_kernel");
+    return (int)(eb < cap ? eb : cap);
+}
+
+// scan -> fill -> sort of the inverse index; `counted` says the sample kernel already took the slots
+template <typename TA, typename CT>
+int launch_binning(const Params& p, bool counted, cudaStream_t st) {
+    const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
+    const int egrid = elementwise_grid(samples);
+    if (!counted) {
+        msda_bin_count_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+        MSDA_LAUNCHED("msda_bin_count_kernel");
+    }
     msda_bin_scan_kernel<<<p.N * p.M, 1024, 0, st>>>(p);
     MSDA_LAUNCHED("msda_bin_scan_kernel");
     msda_bin_fill_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
     MSDA_LAUNCHED("msda_bin_fill_kernel");
-    const long long bins = (long long)p.N * p.M * p.sb_max;
-    const long long sb = ceil_div(bins, kThreads / 8);
-    const long long scap = (long long)num_sms() * 8;
-    msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
-    MSDA_LAUNCHED("msda_bin_sort_small_kernel");
+    {
+        const long long spans = (long long)p.N * p.M * ceil_div(p.sb_max, 32);
+        const long long sb = ceil_div(spans, kThreads / 32);
+        const long long scap = (long long)num_sms() * 8;
+        msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
+        MSDA_LAUNCHED("msda_bin_sort_small_kernel");
+    }
     msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
     MSDA_LAUNCHED("msda_bin_sort_big_kernel");
     return MSDA_OK;
 }
 
-template <typename T, int G>
-int launch_grad_value_tile(const Params& p, cudaStream_t st) {
-    auto k = msda_grad_value_tile_kernel<T, G>;
-    const long long tiles = (long long)p.N * p.M * ceil_div(p.S, kThreads / G);
-    k<<<persistent_grid(k, tiles), kThreads, 0, st>>>(p);
-    MSDA_LAUNCHED("msda_grad_value_tile_kernel");
+template <typename T, int VEC, int G>
+int launch_grad_value_walk(const Params& p, cudaStream_t st) {
+    auto k = msda_grad_value_walk_kernel<T, VEC, G>;
+    // tiles per (frame, head) are only known on the device; S / 8 bounds them from above
+    const long long tiles = (long long)p.N * p.M * (p.S / 8 + p.L);
+    k<<<persistent_grid(k, kGThreads, tiles), kGThreads, 0, st>>>(p);
+    MSDA_LAUNCHED("msda_grad_value_walk_kernel");
     return MSDA_OK;
-}
-
-template <typename T>
-int launch_grad_value_tile_g(const Params& p, int G, cudaStream_t st) {
-    switch (G) {
-        case 4: return launch_grad_value_tile<T, 4>(p, st);
-        case 8: return launch_grad_value_tile<T, 8>(p, st);
-        default: return launch_grad_value_tile<T, 16>(p, st);
-    }
 }
 
 template <typename T, typename CT>
@@ -263,9 +266,68 @@ int launch_grad_value_generic(const Params& p, cudaStream_t st) {
     return MSDA_OK;
 }
 
+// ---- (dtype, VEC, G, P) dispatch tables ------------------------------------------------------
+#define MSDA_FOR_P(CALL, T, TA, VEC, G)                         \
+    (p.P == 4 ? CALL<T, TA, VEC, G, 4>(p, st) : CALL<T, TA, VEC, G, 8>(p, st))
+
+template <typename TA>
+int dispatch_fwd_tile(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {
+    if (vdt == MSDA_F32) {
+        if constexpr (std::is_same<TA, float>::value) {
+            switch (pl.g) {
+                case 4: return MSDA_FOR_P(launch_fwd_tile, float, float, 4, 4);
+                case 8: return MSDA_FOR_P(launch_fwd_tile, float, float, 4, 8);
+                default: return MSDA_FOR_P(launch_fwd_tile, float, float, 4, 16);
+            }
+        }
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fp32 values need fp32 locations");
+    }
+    using B = __nv_bfloat16;
+    if (pl.vec == 4) return MSDA_FOR_P(launch_fwd_tile, B, TA, 4, 8);
+    switch (pl.g) {
+        case 4: return MSDA_FOR_P(launch_fwd_tile, B, TA, 8, 4);
+        case 8: return MSDA_FOR_P(launch_fwd_tile, B, TA, 8, 8);
+        default: return MSDA_FOR_P(launch_fwd_tile, B, TA, 8, 16);
+    }
+}
+
+template <typename TA>
+int dispatch_bwd_sample_tile(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {
+    if (vdt == MSDA_F32) {
+        if constexpr (std::is_same<TA, float>::value) {
+            switch (pl.g) {
+                case 4: return MSDA_FOR_P(launch_bwd_sample_tile, float, float, 4, 4);
+                case 8: return MSDA_FOR_P(launch_bwd_sample_tile, float, float, 4, 8);
+                default: return MSDA_FOR_P(launch_bwd_sample_tile, float, float, 4, 16);
+            }
+        }
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fp32 values need fp32 locations");
+    }
+    using B = __nv_bfloat16;
+    if (pl.vec == 4) return MSDA_FOR_P(launch_bwd_sample_tile, B, TA, 4, 8);
+    switch (pl.g) {
+        case 4: return MSDA_FOR_P(launch_bwd_sample_tile, B, TA, 8, 4);
+        case 8: return MSDA_FOR_P(launch_bwd_sample_tile, B, TA, 8, 8);
+        default: return MSDA_FOR_P(launch_bwd_sample_tile, B, TA, 8, 16);
+    }
+}
+
+int dispatch_grad_value_walk(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {
+    if (vdt == MSDA_F32) {
+        switch (pl.wg) {
+            case 4: return launch_grad_value_walk<float, 4, 4>(p, st);
+            case 8: return launch_grad_value_walk<float, 4, 8>(p, st);
+            default: return launch_grad_value_walk<float, 4, 16>(p, st);
+        }
+    }
+    using B = __nv_bfloat16;
+    if (pl.wvec == 4) return pl.wg == 8 ? launch_grad_value_walk<B, 4, 8>(p, st) : launch_grad_value_walk<B, 4, 16>(p, st);
+    return launch_grad_value_walk<B, 8, 16>(p, st);
+}
+
 // workspace layout (bytes, every region 256-byte aligned)
 struct WsLayout {
-    size_t bin_off, big, pos, entries, total;
+    size_t bin_off, counts, big, pos, entries, total;
     int sb_max, big_cap;
 };
 
@@ -274,33 +336,36 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
     WsLayout w;
     const size_t samples = (size_t)N * Lq * M * L * P;
-    w.sb_max = 2 * S + 2 * L;  // sum (H+1)(W+1) = S + sum H + sum W + L <= 2S + 2L
+    // sub-bins per (frame, head): sum_l nb_l * nch_l with nb_l = (H_l+1)(W_l+1) and
+    // nch_l < 2 * (Lq*P / (6 nb_l) + 1)  =>  < L*Lq*P/3 + 2 * sum nb_l,  sum nb_l <= 2S + 2L
+    w.sb_max = (int)((long long)L * Lq * P / 3 + 4LL * S + 4LL * L + 1);
     w.big_cap = (int)(samples / (kBigBin + 1) + 1);
     const size_t entry = vdt == MSDA_F64 ? sizeof(Entry<double>) : sizeof(Entry<float>);
     w.bin_off = 0;
-    // the big-bin counter sits right behind the bin table so one memset clears both
-    w.big = (size_t)N * M * (w.sb_max + 1) * sizeof(uint32_t);
-    w.pos = align256(w.big + (1 + 2 * (size_t)w.big_cap) * sizeof(uint32_t));
+    // the big-list counter sits right behind the bin table so one memset clears both
+    w.counts = (size_t)N * M * (w.sb_max + 1) * sizeof(uint32_t);
+    w.big = align256(w.counts + 4 * sizeof(uint32_t));
+    w.pos = align256(w.big + 2 * (size_t)w.big_cap * sizeof(uint32_t));
     w.entries = align256(w.pos + samples * sizeof(uint32_t));
     w.total = align256(w.entries + samples * entry);
     return w;
 }
 
 template <typename T, typename TA, typename CT>
-int backward_typed(Params& p, int G, cudaStream_t st) {
+int backward_typed(Params& p, const Plan& pl, int vdt, cudaStream_t st) {
     int rc;
-    if (G) {
-        if constexpr (!std::is_same<T, double>::value) {
-            if ((rc = launch_bwd_sample_tile_g<T, TA>(p, G, st))) return rc;
+    bool tile = pl.tile;
+    if constexpr (std::is_same<T, double>::value || std::is_same<T, __half>::value) tile = false;
+    if (tile) {
+        if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
+            if ((rc = dispatch_bwd_sample_tile<TA>(p, pl, vdt, st))) return rc;
         }
     } else {
         if ((rc = launch_bwd_sample_generic<T, TA, CT>(p, st))) return rc;
     }
     if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) return MSDA_OK;
-    if ((rc = launch_binning<TA, CT>(p, st))) return rc;
-    if (G) {
-        if constexpr (!std::is_same<T, double>::value) return launch_grad_value_tile_g<T>(p, G, st);
-    }
+    if ((rc = launch_binning<TA, CT>(p, /*counted=*/tile, st))) return rc;
+    if (tile) return dispatch_grad_value_walk(p, pl, vdt, st);
     return launch_grad_value_generic<T, CT>(p, st);
 }
 
@@ -334,23 +399,25 @@ int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int6
     p.id_shift = id_shift_for(p.LP);
     p.flags = flags;
 
-    int G = tile_group(D, value_dtype, flags);
-    if (G && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight))) G = 0;
+    Plan pl = make_plan(D, P, value_dtype, flags);
+    if (pl.tile && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight)))
+        pl.tile = false;
+    if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;   // descriptor holds a 28-bit pixel index
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {
         case MSDA_F32:
-            return G ? launch_fwd_tile_g<float, float>(p, G, st) : launch_fwd_generic<float, float, float>(p, st);
+            return pl.tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st)
+                           : launch_fwd_generic<float, float, float>(p, st);
         case MSDA_BF16:
             if (aux32)
-                return G ? launch_fwd_tile_g<__nv_bfloat16, float>(p, G, st)
-                         : launch_fwd_generic<__nv_bfloat16, float, float>(p, st);
-            return G ? launch_fwd_tile_g<__nv_bfloat16, __nv_bfloat16>(p, G, st)
-                     : launch_fwd_generic<__nv_bfloat16, __nv_bfloat16, float>(p, st);
+                return pl.tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st)
+                               : launch_fwd_generic<__nv_bfloat16, float, float>(p, st);
+            return pl.tile ? dispatch_fwd_tile<__nv_bfloat16>(p, pl, value_dtype, st)
+                           : launch_fwd_generic<__nv_bfloat16, __nv_bfloat16, float>(p, st);
         case MSDA_F16:
-            if (aux32)
-                return G ? launch_fwd_tile_g<__half, float>(p, G, st) : launch_fwd_generic<__half, float, float>(p, st);
-            return G ? launch_fwd_tile_g<__half, __half>(p, G, st) : launch_fwd_generic<__half, __half, float>(p, st);
+            return aux32 ? launch_fwd_generic<__half, float, float>(p, st)
+                         : launch_fwd_generic<__half, __half, float>(p, st);
         default:
             return launch_fwd_generic<double, double, double>(p, st);
     }
@@ -381,8 +448,8 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
     if (rc) return rc;
     if (!grad_output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null gradient pointer");
-    if ((flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) &&
-        !(value_dtype == MSDA_F32 && tile_group(D, value_dtype, flags)))
+    Plan pl = make_plan(D, P, value_dtype, flags);
+    if ((flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) && !(value_dtype == MSDA_F32 && pl.tile))
         return fail(MSDA_ERR_UNSUPPORTED, "the atomic A/B arm exists for fp32 tile shapes only");
     const int LP = L * P;
     const int shift = id_shift_for(LP);
@@ -409,31 +476,32 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
     if (need_ws) {
         char* base = static_cast<char*>(workspace);
         p.bin_off = reinterpret_cast<uint32_t*>(base + w.bin_off);
+        p.counts = reinterpret_cast<uint32_t*>(base + w.counts);
         p.big_bins = reinterpret_cast<uint32_t*>(base + w.big);
         p.pos = reinterpret_cast<uint32_t*>(base + w.pos);
         p.entries = base + w.entries;
-        MSDA_CUDA(cudaMemsetAsync(base + w.bin_off, 0, w.big + sizeof(uint32_t), st));
+        MSDA_CUDA(cudaMemsetAsync(base + w.bin_off, 0, w.counts + 4 * sizeof(uint32_t), st));
         ++g_launches;
     } else {
         MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)N * S * M * D * dtype_size(value_dtype), st));
         ++g_launches;
     }
 
-    int G = tile_group(D, value_dtype, flags);
-    if (G && !(aligned16(value) && aligned16(grad_output) && aligned16(grad_value) && aligned16(sampling_loc) &&
-               aligned16(attn_weight) && aligned16(grad_sampling_loc) && aligned16(grad_attn_weight)))
-        G = 0;
+    if (pl.tile && !(aligned16(value) && aligned16(grad_output) && aligned16(grad_value) && aligned16(sampling_loc) &&
+                     aligned16(attn_weight) && aligned16(grad_sampling_loc) && aligned16(grad_attn_weight)))
+        pl.tile = false;
+    if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {
-        case MSDA_F32: return backward_typed<float, float, float>(p, G, st);
+        case MSDA_F32: return backward_typed<float, float, float>(p, pl, value_dtype, st);
         case MSDA_BF16:
-            return aux32 ? backward_typed<__nv_bfloat16, float, float>(p, G, st)
-                         : backward_typed<__nv_bfloat16, __nv_bfloat16, float>(p, G, st);
+            return aux32 ? backward_typed<__nv_bfloat16, float, float>(p, pl, value_dtype, st)
+                         : backward_typed<__nv_bfloat16, __nv_bfloat16, float>(p, pl, value_dtype, st);
         case MSDA_F16:
-            return aux32 ? backward_typed<__half, float, float>(p, G, st)
-                         : backward_typed<__half, __half, float>(p, G, st);
-        default: return backward_typed<double, double, double>(p, 0, st);
+            return aux32 ? backward_typed<__half, float, float>(p, pl, value_dtype, st)
+                         : backward_typed<__half, __half, float>(p, pl, value_dtype, st);
+        default: return backward_typed<double, double, double>(p, pl, value_dtype, st);
     }
 }
 

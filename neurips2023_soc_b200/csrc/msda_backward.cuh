@@ -37,7 +37,7 @@
 //     Results are bit-identical from run to run.
 #pragma once
 
-#include "msda_common.cuh"
+#include "msda_tiles.cuh"
 
 namespace msda {
 
@@ -81,24 +81,27 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
     if constexpr (G >= 2) exchange_halve<NV * 1 / G, 1>(v, gl & 1);
 }
 
-template <int NG>
-struct BwdSmem {
-    int4 off[NG * kDescStride];
-    float4 geo[NG * kDescStride];   // lh, lw, a, level index (int bits)
-};
+#ifndef MSDA_BWD_MIN_BLOCKS
+#define MSDA_BWD_MIN_BLOCKS 2
+#endif
 
-template <typename T, typename TA, int G, bool ATOMIC>
-__global__ void __launch_bounds__(kThreads, 2) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
-    constexpr int VEC = Elem<T>::kVec;
-    constexpr int NG = kThreads / G;
-    constexpr int DPT = NG * kSC / kThreads;
+// COUNT: the staging threads also take each accepted sample's slot in the inverse index of
+// part B (integer atomics, overlapped with the gather).  ATOMIC: bench-only A/B arm that
+// scatters grad_value with 128-bit fp32 reductions like the reference does with scalar ones.
+template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool ATOMIC>
+__global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
+    using TS = TileShape<G>;
+    constexpr int NG = TS::NG;
     constexpr int NSL = kSC / G;               // finished samples per lane after the reduction
+    constexpr int LPC = (P >= kSC) ? 1 : kSC / P;
+    constexpr int PPC = (P >= kSC) ? kSC : P;
     static_assert(G <= kSC, "a lane must end up with at least one whole sample");
+    static_assert(!ATOMIC || (VEC == 4 && sizeof(T) == 4), "atomic arm is fp32 only");
 
     __shared__ Level lv[kMaxLevels];
     __shared__ TileMap tm;
     __shared__ int s_sb, s_sq;
-    __shared__ BwdSmem<NG> sm;
+    __shared__ uint4 desc[2][NG * kDescStride];
 
     const int tile_q = NG * rounds;
     load_levels(p, lv, &s_sb, &s_sq);
@@ -111,122 +114,117 @@ __global__ void __launch_bounds__(kThreads, 2) msda_bwd_sample_tile_kernel(const
     TA* __restrict__ gloc = static_cast<TA*>(p.grad_loc);
     TA* __restrict__ gattn = static_cast<TA*>(p.grad_attn);
 
-    const int tid = threadIdx.x;
-    const int grp = tid / G, gl = tid % G;
-    const int st_s = tid % kSC, st_j0 = tid / kSC;
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     const int row_elems = p.M * p.D;
     const int total_tiles = p.N * p.M * tm.qtiles;
 
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, lv, &tm, t, tile_q);
-        const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
-        const T* vbase = value + frame_off;
+    Work cur{(int)blockIdx.x, 0, 0};
+    if (cur.t >= total_tiles) return;
+    Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
+    Staged<TS::DPT> st;
+    stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
+    stage_build<G, P, COUNT>(st, p, lv, tl, cur, desc[0]);
+    __syncthreads();
 
-        for (int r = 0; r < rounds; ++r) {
-            const int q_mine = tile_query(p, &tm, tl, r * NG + grp);
-            const size_t qm_mine = ((size_t)tl.n * p.Lq + (q_mine < 0 ? 0 : q_mine)) * p.M + tl.m;
-            float g[VEC];
+    int buf = 0;
+    float g[VEC];
+    while (true) {
+        const Work nxt = next_work(cur, rounds, p.LP);
+        const bool has_next = nxt.t < total_tiles;
+        Tile ntl = tl;
+        if (has_next) {
+            if (nxt.t != cur.t) ntl = decode_tile(p, lv, &tm, nxt.t, tile_q);
+            stage_load<TA, G>(st, p, &tm, ntl, nxt, loc, attn);
+        }
+
+        const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);
+        const size_t qm_mine = ((size_t)tl.n * p.Lq + (q_mine < 0 ? 0 : q_mine)) * p.M + tl.m;
+        if (cur.c0 == 0) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) g[i] = 0.f;
-            if (q_mine >= 0) load_vec(gout + qm_mine * p.D + gl * VEC, g);
+            if (q_mine >= 0) load_row<T, VEC>(gout + qm_mine * p.D + gl * VEC, g);
+        }
+        const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
+        const T* vbase = value + frame_off;
+        const uint4* drow = desc[buf] + grp * kDescStride;
+        const int l0 = cur.c0 / P;
 
-            for (int c0 = 0; c0 < p.LP; c0 += kSC) {
-                __syncthreads();
-                const int sg = c0 + st_s;
-                const bool s_ok = sg < p.LP;
-                const int l = s_ok ? sg / p.P : 0;
-                const Level L_ = lv[l];
+        // per-lane partial corner dot products d_k = <g, v_k> for the chunk's 16 samples
+        float part[4 * kSC];
 #pragma unroll
-                for (int k = 0; k < DPT; ++k) {
-                    const int j = st_j0 + k * (kThreads / kSC);
-                    const int q = tile_query(p, &tm, tl, r * NG + j);
-                    int4 o = make_int4(-1, -1, -1, -1);
-                    float4 d = make_float4(0.f, 0.f, 0.f, __int_as_float(l));
-                    if (s_ok && q >= 0) {
-                        const size_t si = (((size_t)tl.n * p.Lq + q) * p.M + tl.m) * p.LP + sg;
-                        const XY<float> xy = load_xy(loc + 2 * si);
-                        const Sample<float> s = locate(xy.x, xy.y, L_.H, L_.W);
-                        if (s.ok) {
-                            int pix[4];
-                            corner_pixels(s, L_, pix);
-                            o.x = pix[0] < 0 ? -1 : pix[0] * row_elems;
-                            o.y = pix[1] < 0 ? -1 : pix[1] * row_elems;
-                            o.z = pix[2] < 0 ? -1 : pix[2] * row_elems;
-                            o.w = pix[3] < 0 ? -1 : pix[3] * row_elems;
-                            d.x = s.lh; d.y = s.lw;
-                            d.z = Elem<TA>::to_f(__ldg(attn + si));
-                        }
-                    }
-                    sm.off[j * kDescStride + st_s] = o;
-                    sm.geo[j * kDescStride + st_s] = d;
+        for (int lc = 0; lc < LPC; ++lc) {
+            const int l = min(l0 + lc, p.L - 1);          // slots past L*P carry no corner bits
+            const LevelPitch lp = level_pitch(lv[l], row_elems);
+            const int sbase = (P >= kSC) ? 0 : lc * PPC;
+#pragma unroll
+            for (int pp = 0; pp < PPC; ++pp) {
+                const int s = sbase + pp;
+                const uint4 d = drow[s];
+                const long long o0 = lp.base + (long long)(d.x & 0x0fffffffu) * row_elems;
+                const T* c0p = vbase + o0;
+                const T* c2p = c0p + lp.wrow;
+                float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
+                if (d.x & (1u << 28)) load_row<T, VEC>(c0p, v0);
+                if (d.x & (2u << 28)) load_row<T, VEC>(c0p + row_elems, v1);
+                if (d.x & (4u << 28)) load_row<T, VEC>(c2p, v2);
+                if (d.x & (8u << 28)) load_row<T, VEC>(c2p + row_elems, v3);
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    d0 = fmaf(g[i], v0[i], d0);
+                    d1 = fmaf(g[i], v1[i], d1);
+                    d2 = fmaf(g[i], v2[i], d2);
+                    d3 = fmaf(g[i], v3[i], d3);
                 }
-                __syncthreads();
-
-                // per-lane partial corner dot products for the chunk's 16 samples
-                float part[4 * kSC];
+                part[4 * s + 0] = d0; part[4 * s + 1] = d1;
+                part[4 * s + 2] = d2; part[4 * s + 3] = d3;
+                if constexpr (ATOMIC) {
+                    const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
+                    const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+                    const float w[4] = {ah * hw, ah * lw, al * hw, al * lw};
+                    float* gv = static_cast<float*>(p.grad_value) + frame_off + o0;
+                    const long long oo[4] = {0, row_elems, lp.wrow, (long long)lp.wrow + row_elems};
 #pragma unroll
-                for (int s = 0; s < kSC; ++s) {
-                    const int4 o = sm.off[grp * kDescStride + s];
-                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                    if (o.x >= 0) load_vec(vbase + o.x, v0);
-                    if (o.y >= 0) load_vec(vbase + o.y, v1);
-                    if (o.z >= 0) load_vec(vbase + o.z, v2);
-                    if (o.w >= 0) load_vec(vbase + o.w, v3);
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        d0 = fmaf(g[i], v0[i], d0);
-                        d1 = fmaf(g[i], v1[i], d1);
-                        d2 = fmaf(g[i], v2[i], d2);
-                        d3 = fmaf(g[i], v3[i], d3);
-                    }
-                    part[4 * s + 0] = d0; part[4 * s + 1] = d1;
-                    part[4 * s + 2] = d2; part[4 * s + 3] = d3;
-                    if constexpr (ATOMIC) {
-                        // bench-only A/B arm: the reference's scatter with 128-bit fp32 reductions
-                        // (order-dependent rounding => NOT deterministic; never the default)
-                        static_assert(!ATOMIC || VEC == 4, "atomic arm is fp32 only");
-                        const float4 d = sm.geo[grp * kDescStride + s];
-                        const float hh = 1.f - d.x, hw = 1.f - d.y;
-                        const float w[4] = {hh * hw * d.z, hh * d.y * d.z, d.x * hw * d.z, d.x * d.y * d.z};
-                        const int oo[4] = {o.x, o.y, o.z, o.w};
-                        float* gv = static_cast<float*>(p.grad_value) + frame_off;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (oo[k] >= 0 && q_mine >= 0)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gv + oo[k]),
-                                             "f"(w[k] * g[0]), "f"(w[k] * g[1]), "f"(w[k] * g[2]), "f"(w[k] * g[3])
-                                             : "memory");
-                    }
-                }
-                reduce_scatter<G>(part, gl);
-
-                if (q_mine >= 0) {
-#pragma unroll
-                    for (int i = 0; i < NSL; ++i) {
-                        const int s = gl * NSL + i;
-                        const int sgo = c0 + s;
-                        if (sgo < p.LP) {
-                            const float4 d = sm.geo[grp * kDescStride + s];
-                            const int ls = __float_as_int(d.w);
-                            const float Hf = (float)lv[ls].H, Wf = (float)lv[ls].W;
-                            const float lh = d.x, lw = d.y, a = d.z;
-                            const float hh = 1.f - lh, hw = 1.f - lw;
-                            const float d0 = part[4 * i], d1 = part[4 * i + 1], d2 = part[4 * i + 2], d3 = part[4 * i + 3];
-                            const float ga = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
-                            const float gx = hh * (d1 - d0) + lh * (d3 - d2);
-                            const float gy = hw * (d2 - d0) + lw * (d3 - d1);
-                            const size_t si = qm_mine * p.LP + sgo;
-                            gattn[si] = Elem<TA>::from_f(ga);
-                            gloc[2 * si] = Elem<TA>::from_f(Wf * a * gx);
-                            gloc[2 * si + 1] = Elem<TA>::from_f(Hf * a * gy);
-                        }
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if ((d.x >> (28 + k)) & 1u)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gv + oo[k]),
+                                         "f"(w[k] * g[0]), "f"(w[k] * g[1]), "f"(w[k] * g[2]), "f"(w[k] * g[3])
+                                         : "memory");
                 }
             }
         }
+        reduce_scatter<G>(part, gl);
+
+        if (q_mine >= 0) {
+#pragma unroll
+            for (int i = 0; i < NSL; ++i) {
+                const int s = gl * NSL + i;
+                const int sgo = cur.c0 + s;
+                if (sgo < p.LP) {
+                    const uint4 d = drow[s];
+                    const Level& L_ = lv[sgo / P];
+                    const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
+                    const float hh = 1.f - lh, hw = 1.f - lw;
+                    const float d0 = part[4 * i], d1 = part[4 * i + 1], d2 = part[4 * i + 2], d3 = part[4 * i + 3];
+                    const float ga = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
+                    const float gx = hh * (d1 - d0) + lh * (d3 - d2);
+                    const float gy = hw * (d2 - d0) + lw * (d3 - d1);
+                    const size_t si = qm_mine * p.LP + sgo;
+                    gattn[si] = Elem<TA>::from_f(ga);
+                    gloc[2 * si] = Elem<TA>::from_f((float)L_.W * a * gx);
+                    gloc[2 * si + 1] = Elem<TA>::from_f((float)L_.H * a * gy);
+                }
+            }
+        }
+
+        if (has_next) stage_build<G, P, COUNT>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        __syncthreads();
+        if (!has_next) break;
+        cur = nxt;
+        tl = ntl;
+        buf ^= 1;
     }
 }
 
@@ -328,15 +326,15 @@ __global__ void __launch_bounds__(kThreads) msda_bin_count_kernel(const Params p
         const Sample<CT> s = locate(xy.x, xy.y, L_.H, L_.W);
         uint32_t slot = kRejected;
         if (s.ok) {
-            const int bin = L_.bin_start + (s.h_lo + 1) * (L_.W + 1) + (s.w_lo + 1);
+            const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
             slot = atomicAdd(p.bin_off + (size_t)(r.n * p.M + r.m) * (p.sb_max + 1) + bin, 1u);
         }
         p.pos[si] = slot;
     }
 }
 
-// One CTA per (frame, head): in-place exclusive scan of the bin counts; bins with more
-// than kBigBin entries are appended to the big-bin list.
+// One CTA per (frame, head): in-place exclusive scan of the sub-bin counts.  Sub-bins with
+// more than kBigBin entries are appended to the big list (sorted by one CTA each).
 __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
@@ -352,10 +350,10 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
         const uint32_t c = data[i];
         sum += c;
         if (c > (uint32_t)kBigBin) {
-            const uint32_t k = atomicAdd(p.big_bins, 1u);
+            const uint32_t k = atomicAdd(p.counts + 0, 1u);
             if (k < (uint32_t)p.big_cap) {
-                p.big_bins[1 + 2 * k] = (uint32_t)nm;
-                p.big_bins[2 + 2 * k] = (uint32_t)i;
+                p.big_bins[2 * k] = (uint32_t)nm;
+                p.big_bins[2 * k + 1] = (uint32_t)i;
             }
         }
     }
@@ -404,7 +402,7 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
         const Level L_ = lv[r.l];
         const XY<CT> xy = load_xy(loc + 2 * si);
         const Sample<CT> s = locate(xy.x, xy.y, L_.H, L_.W);
-        const int bin = L_.bin_start + (s.h_lo + 1) * (L_.W + 1) + (s.w_lo + 1);
+        const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
         const size_t nm = (size_t)r.n * p.M + r.m;
         const uint32_t base = p.bin_off[nm * (p.sb_max + 1) + bin];
         Entry<CT> e;
@@ -444,6 +442,10 @@ __device__ __forceinline__ void sort_in_lanes(Entry<CT>* base, const uint32_t cn
     if (sub < (int)cnt) base[sub] = e;
 }
 
+// Sub-bins of up to 32 entries, sorted in place.  A warp takes 32 consecutive sub-bins: their
+// offsets are read with one coalesced load and handed around with shuffles; sub-bins of 2..8
+// entries are sorted four at a time by the warp's 8-lane segments, those of 9..32 by the
+// whole warp.
 template <typename CT>
 __global__ void __launch_bounds__(kThreads) msda_bin_sort_small_kernel(const Params p) {
     __shared__ Level lv[kMaxLevels];
@@ -452,45 +454,34 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_small_kernel(const Par
     Entry<CT>* __restrict__ entries = static_cast<Entry<CT>*>(p.entries);
     const int SB = s_sb;
     const size_t per_nm = (size_t)p.Lq * p.LP;
-    const size_t nbins = (size_t)p.N * p.M * SB;
-    const int lane = threadIdx.x & 31;
-    // phase 1: 8-lane segments, bins of 2..8 entries
-    {
-        const int sub = lane & 7;
-        const uint32_t mask = 0xffu << (lane & 24);
-        const size_t segs = (size_t)gridDim.x * (kThreads / 8);
-        for (size_t b = (size_t)blockIdx.x * (kThreads / 8) + threadIdx.x / 8; b < nbins; b += segs) {
-            const size_t nm = b / SB;
-            const int bin = (int)(b - nm * SB);
-            const uint32_t* off = p.bin_off + nm * (p.sb_max + 1) + bin;
-            const uint32_t beg = off[0], cnt = off[1] - beg;
-            if (cnt >= 2 && cnt <= 8) sort_in_lanes<CT, 8>(entries + nm * per_nm + beg, cnt, sub, mask);
+    const int lane = threadIdx.x & 31, sub = lane & 7, seg = lane >> 3;
+    const uint32_t segmask = 0xffu << (lane & 24);
+    const int spans = (SB + 31) / 32;                      // 32-sub-bin spans per (frame, head)
+    const size_t total = (size_t)p.N * p.M * spans;
+    const size_t warps = (size_t)gridDim.x * (kThreads / 32);
+    for (size_t w = (size_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32; w < total; w += warps) {
+        const size_t nm = w / spans;
+        const int b = (int)(w - nm * spans) * 32 + lane;
+        const uint32_t* off = p.bin_off + nm * (p.sb_max + 1);
+        uint32_t beg = 0, cnt = 0;
+        if (b < SB) {
+            beg = off[b];
+            cnt = off[b + 1] - beg;
         }
-    }
-    // phase 2: whole warps, bins of 9..32 entries
-    {
-        const size_t warps = (size_t)gridDim.x * (kThreads / 32);
-        const size_t span = (nbins + 31) / 32;
-        for (size_t w = (size_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32; w < span; w += warps) {
-            const size_t b = w * 32 + lane;
-            uint32_t beg = 0, cnt = 0;
-            size_t nm = 0;
-            if (b < nbins) {
-                nm = b / SB;
-                const int bin = (int)(b - nm * SB);
-                const uint32_t* off = p.bin_off + nm * (p.sb_max + 1) + bin;
-                beg = off[0];
-                cnt = off[1] - beg;
-            }
-            uint32_t todo = __ballot_sync(0xffffffffu, cnt > 8 && cnt <= (uint32_t)kBigBin);
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t bbeg = __shfl_sync(0xffffffffu, beg, src);
-                const uint32_t bcnt = __shfl_sync(0xffffffffu, cnt, src);
-                const size_t bnm = __shfl_sync(0xffffffffu, (unsigned long long)nm, src);
-                sort_in_lanes<CT, 32>(entries + bnm * per_nm + bbeg, bcnt, lane, 0xffffffffu);
-            }
+        Entry<CT>* ent = entries + nm * per_nm;
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t sbeg = __shfl_sync(0xffffffffu, beg, seg * 8 + j);
+            const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, seg * 8 + j);
+            if (scnt >= 2 && scnt <= 8) sort_in_lanes<CT, 8>(ent + sbeg, scnt, sub, segmask);
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, cnt > 8 && cnt <= (uint32_t)kBigBin);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t bbeg = __shfl_sync(0xffffffffu, beg, src);
+            const uint32_t bcnt = __shfl_sync(0xffffffffu, cnt, src);
+            sort_in_lanes<CT, 32>(ent + bbeg, bcnt, lane, 0xffffffffu);
         }
     }
 }
@@ -503,10 +494,10 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_big_kernel(const Param
     __shared__ Entry<CT> buf[CAP];
     Entry<CT>* __restrict__ entries = static_cast<Entry<CT>*>(p.entries);
     const size_t per_nm = (size_t)p.Lq * p.LP;
-    const uint32_t nbig = min(p.big_bins[0], (uint32_t)p.big_cap);
+    const uint32_t nbig = min(p.counts[0], (uint32_t)p.big_cap);
     for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
-        const size_t nm = p.big_bins[1 + 2 * i];
-        const uint32_t bin = p.big_bins[2 + 2 * i];
+        const size_t nm = p.big_bins[2 * i];
+        const uint32_t bin = p.big_bins[2 * i + 1];
         const uint32_t* off = p.bin_off + nm * (p.sb_max + 1) + bin;
         const uint32_t beg = off[0], cnt = off[1] - beg;
         Entry<CT>* g = entries + nm * per_nm + beg;
@@ -539,77 +530,247 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_big_kernel(const Param
 }
 
 // ---- gather ---------------------------------------------------------------------------
+//
+// Tile kernel.  Regrouping the scatter by BIN instead of by destination pixel means every
+// sample's grad_output row is read once, not four times: for bin b
+//      G_k[b] = sum_{e in b} w_k(e) a(e) grad_output[q(e)]        k = 1..4  (the four corners)
+// and pixel (y, x) receives  G_1[(y+1,x+1)] + G_2[(y+1,x)] + G_3[(y,x+1)] + G_4[(y,x)].
+// A CTA owns a TH x 8 pixel tile of one level, frame and head.  A group of G lanes walks one
+// bin row of the tile left to right, keeps G_2/G_4 of the previous bin in registers and emits
+//      T[y][x] = G_1[cur] + G_2[prev]  (bin row y+1)      B[y][x] = G_3[cur] + G_4[prev]  (bin row y)
+// into two shared-memory tiles with plain stores -- every element is written exactly once, so
+// there is nothing to zero and nothing to race on.  After one barrier the CTA stores T + B
+// with vector stores.
+// The entries of the bins of one row segment are contiguous in memory (bins are numbered
+// row-major and the scan is over bin index), so the walk is a linear stream: the nine bin
+// boundaries are read up front, entries are fetched G at a time one batch ahead, and the
+// owner lane of an entry forms its four weight products and its bin once for the group.
+// In dense levels (many entries per bin) the 32/G groups of a warp share each bin -- each takes
+// a contiguous share of its entries -- and combine their sums with shuffles in a fixed order.
+constexpr int kGThreads = 128;
+constexpr int kGTileW = 8;
+constexpr int kGBounds = kGTileW + 2;   // boundaries of the up to 9 bins of a row segment
 
-template <typename T, int G>
-__global__ void __launch_bounds__(kThreads) msda_grad_value_tile_kernel(const Params p) {
-    constexpr int VEC = Elem<T>::kVec;
-    constexpr int NG = kThreads / G;           // grad_value rows per CTA pass
+template <int VEC>
+struct BinAcc {
+    float g1[VEC], g2[VEC], g3[VEC], g4[VEC];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g1[i] = g2[i] = g3[i] = g4[i] = 0.f;
+    }
+};
+
+__device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restrict__ ent, uint32_t pos, uint32_t end) {
+    Entry<float> e;
+    e.id = 0; e.lh = e.lw = e.a = 0.f;
+    if (pos < end) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(ent + pos));
+        e.id = t.x; e.lh = __uint_as_float(t.y); e.lw = __uint_as_float(t.z); e.a = __uint_as_float(t.w);
+    }
+    return e;
+}
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const Params p) {
+    constexpr int D = VEC * G;
+    constexpr int NGRP = kGThreads / G;          // groups per CTA
+    constexpr int GW = 32 / G;                   // groups per warp
+    constexpr int BR = (512 / D) < 2 ? 2 : (512 / D);   // bin rows per tile
+    constexpr int TH = BR - 1, TW = kGTileW;
+    constexpr int STEP = 4;                      // grad_output rows in flight per lane
+
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
+    __shared__ int tstart[kMaxLevels + 1];
+    __shared__ __align__(16) float sT[TH * TW * D];
+    __shared__ __align__(16) float sB[TH * TW * D];
     load_levels(p, lv, &s_sb, &s_sq);
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int l = 0; l < p.L; ++l) {
+            tstart[l] = t;
+            t += ((lv[l].H + TH - 1) / TH) * ((lv[l].W + TW - 1) / TW);
+        }
+        tstart[p.L] = t;
+    }
+    __syncthreads();
 
     const T* __restrict__ gout = static_cast<const T*>(p.grad_out);
     T* __restrict__ gval = static_cast<T*>(p.grad_value);
     const Entry<float>* __restrict__ entries = static_cast<const Entry<float>*>(p.entries);
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int grp = tid / G, gl = tid % G;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid / G, gl = tid % G, gw = lane / G;    // gw: group index inside the warp
     const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
-    const int chunks = (p.S + NG - 1) / NG;
-    const int total_tiles = p.N * p.M * chunks;
+    const int per_nm_tiles = tstart[p.L];
+    const int total_tiles = p.N * p.M * per_nm_tiles;
     const size_t per_nm = (size_t)p.Lq * p.LP;
+    const size_t qstride = (size_t)p.M * p.D;
 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        // coarse levels (end of the pixel order) carry the longest lists: issue them first
-        const int n = t / (chunks * p.M);
-        const int r = t - n * chunks * p.M;
-        const int chunk = chunks - 1 - r / p.M;
+        const int n = t / (per_nm_tiles * p.M);
+        const int r = t - n * per_nm_tiles * p.M;
+        const int lt = per_nm_tiles - 1 - r / p.M;        // coarse (dense) levels first
         const int m = r % p.M;
-        const int s = chunk * NG + grp;
-        if (s >= p.S) continue;               // whole group idle (group-uniform)
+        int l = 0;
+        while (l + 1 < p.L && lt >= tstart[l + 1]) ++l;
+        const Level L_ = lv[l];
+        const int tw = (L_.W + TW - 1) / TW;
+        const int k = lt - tstart[l];
+        const int y0 = (k / tw) * TH, x0 = (k % tw) * TW;
+        const int nb = min(x0 + TW, L_.W) - x0 + 1;       // bins walked per row: x0 .. min(x0+TW, W)
+        // dense: a bin holds enough entries to keep every group of a warp busy
+        const bool dense = GW > 1 && (1 << L_.nch_log2) * kSubBinTarget >= 4 * G * GW;
+
         const size_t nm = (size_t)n * p.M + m;
         const uint32_t* off = p.bin_off + nm * (p.sb_max + 1);
         const Entry<float>* ent = entries + nm * per_nm;
         const T* gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
-        const size_t qstride = (size_t)p.M * p.D;
 
-        float acc[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        const int row_first = dense ? warp : grp;
+        const int row_step = dense ? kGThreads / 32 : NGRP;
+        for (int row = row_first; row < BR; row += row_step) {
+            const int by = y0 + row;
+            if (by > L_.H) break;
+            const bool emit_t = row >= 1;                              // pixel row by-1 is in the tile
+            const bool emit_b = row <= TH - 1 && by <= L_.H - 1;       // pixel row by is in the tile
+            float* const tdst = sT + (row - 1) * TW * D + gl * VEC;
+            float* const bdst = sB + row * TW * D + gl * VEC;
 
-        int l = -1;
-        for (int k = 0; k < p.L; ++k)
-            if (s >= lv[k].start && s < lv[k].start + lv[k].H * lv[k].W) { l = k; break; }
-        if (l >= 0) {
-            const Level L_ = lv[l];
-            const int y = (s - L_.start) / L_.W, x = (s - L_.start) % L_.W;
-            const int b_hi = L_.bin_start + (y + 1) * (L_.W + 1) + x;   // (y+1, x): corner 2; +1: corner 1
-            const int b_lo = L_.bin_start + y * (L_.W + 1) + x;         // (y,   x): corner 4; +1: corner 3
-            const int bins[4] = {b_hi + 1, b_hi, b_lo + 1, b_lo};
+            // entry offsets at the boundaries of the row segment's bins
+            const uint32_t* orow = off + L_.bin_start + ((by * (L_.W + 1) + x0) << L_.nch_log2);
+            uint32_t bb[kGBounds];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t beg = off[bins[c]], end = off[bins[c] + 1];
-                for (uint32_t e0 = beg; e0 < end; e0 += G) {
-                    Entry<float> mine;
-                    mine.id = 0; mine.lh = mine.lw = mine.a = 0.f;
-                    if (e0 + gl < end) mine = ent[e0 + gl];
-                    const float hh = 1.f - mine.lh, hw = 1.f - mine.lw;
-                    const float wsel = (c == 0) ? hh * hw : (c == 1) ? hh * mine.lw : (c == 2) ? mine.lh * hw : mine.lh * mine.lw;
-                    const float wa_mine = wsel * mine.a;
-                    const int nb = min((uint32_t)G, end - e0);
-                    for (int e = 0; e < nb; ++e) {
-                        const uint32_t id = __shfl_sync(gmask, mine.id, e, G);
-                        const float wa = __shfl_sync(gmask, wa_mine, e, G);
-                        const uint32_t q = id >> p.id_shift;
-                        float gv[VEC];
-                        load_vec(gbase + (size_t)q * qstride, gv);
+            for (int j = 0; j < kGBounds; ++j) bb[j] = orow[(j <= nb ? j : nb) << L_.nch_log2];
+
+            BinAcc<VEC> acc;
+            acc.clear();
+            float p2[VEC], p4[VEC];
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(wa, gv[i], acc[i]);
+            for (int i = 0; i < VEC; ++i) p2[i] = p4[i] = 0.f;
+
+            // finish bin `b`: emit the pixel to its left, hand G2/G4 on, start the next bin
+            auto emit = [&](const int b) {
+                if (b > 0 && (!dense || gw == 0)) {
+                    if (emit_t) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) tdst[(b - 1) * D + i] = acc.g1[i] + p2[i];
                     }
+                    if (emit_b) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) bdst[(b - 1) * D + i] = acc.g3[i] + p4[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { p2[i] = acc.g2[i]; p4[i] = acc.g4[i]; }
+                acc.clear();
+            };
+
+            // stream entries [e_beg, e_end): `tagged` entries carry their bin, bins are emitted on change
+            auto stream = [&](const uint32_t e_beg, const uint32_t e_end, int& cur_bin, const bool tagged) {
+                Entry<float> nxt = load_entry(ent, e_beg + gl, e_end);
+                for (uint32_t e0 = e_beg; e0 < e_end; e0 += G) {
+                    const Entry<float> mine = nxt;
+                    nxt = load_entry(ent, e0 + G + gl, e_end);
+                    const int nbat = (int)min((uint32_t)G, e_end - e0);
+                    const float ah = mine.a * (1.f - mine.lh), al = mine.a * mine.lh, hw = 1.f - mine.lw;
+                    const float myw[4] = {ah * hw, ah * mine.lw, al * hw, al * mine.lw};
+                    const uint32_t myq = mine.id >> p.id_shift;
+                    int mybin = 0;
+                    if (tagged) {
+                        const uint32_t pos = e0 + gl;
+#pragma unroll
+                        for (int j = 1; j < kGBounds - 1; ++j) mybin += (j < nb && bb[j] <= pos);
+                    }
+#pragma unroll
+                    for (int c0 = 0; c0 < G; c0 += STEP) {
+                        if (c0 >= nbat) break;
+                        float gv[STEP][VEC], w[STEP][4];
+                        int bin[STEP];
+#pragma unroll
+                        for (int e = 0; e < STEP; ++e) {
+                            const uint32_t q = __shfl_sync(gmask, myq, c0 + e, G);
+                            bin[e] = __shfl_sync(gmask, mybin, c0 + e, G);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) w[e][kk] = __shfl_sync(gmask, myw[kk], c0 + e, G);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) gv[e][i] = 0.f;
+                            if (c0 + e < nbat) load_row<T, VEC>(gbase + (size_t)q * qstride, gv[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < STEP; ++e) {
+                            if (c0 + e < nbat) {
+                                if (tagged) {
+                                    while (cur_bin < bin[e]) emit(cur_bin++);
+                                }
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) {
+                                    acc.g1[i] = fmaf(w[e][0], gv[e][i], acc.g1[i]);
+                                    acc.g2[i] = fmaf(w[e][1], gv[e][i], acc.g2[i]);
+                                    acc.g3[i] = fmaf(w[e][2], gv[e][i], acc.g3[i]);
+                                    acc.g4[i] = fmaf(w[e][3], gv[e][i], acc.g4[i]);
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+
+            if (!dense) {
+                int cur_bin = 0;
+                stream(bb[0], bb[kGBounds - 1], cur_bin, true);      // bb[last] == bb[nb]
+                while (cur_bin < nb) emit(cur_bin++);
+            } else {
+#pragma unroll 1
+                for (int b = 0; b < nb; ++b) {
+                    uint32_t b0 = bb[0], b1 = bb[1];
+#pragma unroll
+                    for (int j = 1; j < kGBounds - 1; ++j)
+                        if (j == b) { b0 = bb[j]; b1 = bb[j + 1]; }
+                    const uint32_t share = (b1 - b0 + GW - 1) / GW;
+                    const uint32_t r0 = min(b1, b0 + gw * share), r1 = min(b1, r0 + share);
+                    int unused = 0;
+                    stream(r0, r1, unused, false);
+                    // fixed-order combine over the GW groups of the warp (lane bits >= log2 G)
+#pragma unroll
+                    for (int d = G; d < 32; d <<= 1) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            acc.g1[i] += __shfl_xor_sync(0xffffffffu, acc.g1[i], d);
+                            acc.g2[i] += __shfl_xor_sync(0xffffffffu, acc.g2[i], d);
+                            acc.g3[i] += __shfl_xor_sync(0xffffffffu, acc.g3[i], d);
+                            acc.g4[i] += __shfl_xor_sync(0xffffffffu, acc.g4[i], d);
+                        }
+                    }
+                    emit(b);
                 }
             }
         }
-        store_vec(gval + ((size_t)n * p.S + s) * qstride + (size_t)m * p.D + gl * VEC, acc);
+        __syncthreads();
+        for (int i = tid; i < TH * TW * G; i += kGThreads) {
+            const int c = i % G, px = (i / G) % TW, py = i / (G * TW);
+            const int y = y0 + py, x = x0 + px;
+            if (y < L_.H && x < L_.W) {
+                float v[VEC];
+                const float* a = sT + (py * TW + px) * D + c * VEC;
+                const float* b = sB + (py * TW + px) * D + c * VEC;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) v[j] = a[j] + b[j];
+                store_row<T, VEC>(gval + ((size_t)n * p.S + L_.start + y * L_.W + x) * qstride + (size_t)m * p.D + c * VEC, v);
+            }
+        }
+        __syncthreads();
+    }
+
+    // value rows that belong to no level (level_start_index with gaps) get a zero gradient
+    for (size_t row = (size_t)blockIdx.x * kGThreads + tid; row < (size_t)p.N * p.S; row += (size_t)gridDim.x * kGThreads) {
+        const int s = (int)(row % p.S);
+        bool covered = false;
+        for (int k = 0; k < p.L; ++k) covered |= (s >= lv[k].start && s < lv[k].start + lv[k].H * lv[k].W);
+        if (!covered) {
+            T* dst = gval + row * qstride;
+            for (size_t i = 0; i < qstride; ++i) dst[i] = Elem<T>::from_f(0.f);
+        }
     }
 }
 
@@ -646,11 +807,13 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_generic_kernel(const
             if (l >= 0) {
                 const Level L_ = lv[l];
                 const int y = (s - L_.start) / L_.W, x = (s - L_.start) % L_.W;
-                const int b_hi = L_.bin_start + (y + 1) * (L_.W + 1) + x;
-                const int b_lo = L_.bin_start + y * (L_.W + 1) + x;
+                const int b_hi = (y + 1) * (L_.W + 1) + x;   // (y+1, x): corner 2; +1: corner 1
+                const int b_lo = y * (L_.W + 1) + x;         // (y,   x): corner 4; +1: corner 3
                 const int bins[4] = {b_hi + 1, b_hi, b_lo + 1, b_lo};
                 for (int c = 0; c < 4; ++c) {
-                    const uint32_t beg = off[bins[c]], end = off[bins[c] + 1];
+                    // all sub-bins of a bin are adjacent and each is sorted by id
+                    const uint32_t beg = off[L_.bin_start + (bins[c] << L_.nch_log2)];
+                    const uint32_t end = off[L_.bin_start + ((bins[c] + 1) << L_.nch_log2)];
                     for (uint32_t e = beg; e < end; ++e) {
                         const Entry<CT> en = ent[e];
                         const CT hh = (CT)1 - en.lh, hw = (CT)1 - en.lw;

@@ -14,12 +14,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace msda {
 
 constexpr int kMaxLevels = 16;   // levels held in shared memory per CTA
 constexpr int kThreads = 256;    // CTA size of the tile kernels
 constexpr int kSC = 16;          // samples staged per chunk (L*P = 16 in every SOC config)
 constexpr int kDescStride = kSC + 1;  // 16 B slots per query in the descriptor arrays (+1: bank skew)
+constexpr int kSubBinTarget = 6;      // aimed-at entries per sub-bin (see Level::nch_log2)
+constexpr int kMaxSubLog2 = 8;
 constexpr int kTileW = 16;       // pyramid query tile: kTileH x kTileW pixels of one level
 constexpr int kTileH = 8;
 constexpr int kTileQ = kTileW * kTileH;
@@ -40,19 +44,25 @@ struct Params {
     uint32_t* bin_off;       // [N*M][sb_max + 1]  counts, then exclusive offsets
     uint32_t* pos;           // [N*Lq*M*L*P]       slot of each sample inside its bin
     void* entries;           // [N*M][Lq*L*P]      per-bin contribution lists
-    uint32_t* big_bins;      // [0] = count, then (nm, bin) pairs of bins with > 32 entries
+    uint32_t* counts;        // [0] entries in big_bins (right behind bin_off so one memset clears both)
+    uint32_t* big_bins;      // (nm, sub-bin) pairs of sub-bins with > 32 entries
     int N, S, M, D, L, Lq, P;
     int LP;                  // L*P
     int id_shift;            // entry id = (q << id_shift) | s,  1<<id_shift >= LP
-    int sb_max;              // 2*S + 2*L: bound on sum_l (H_l+1)(W_l+1)
+    int sb_max;              // bound on the number of sub-bins per (frame, head), see ws_layout()
     int big_cap;             // capacity of big_bins in pairs
     unsigned flags;
 };
 
+// A "bin" is the top-left corner (h_lo+1, w_lo+1) of a sample in the (H+1)x(W+1) grid of a
+// level; every bin is split into 2^nch_log2 sub-bins by the low bits of the query index so
+// that a sub-bin holds about kSubBinTarget entries whatever the level's density.
 struct Level {
     int H, W;
     int start;      // level_start_index[l]
-    int bin_start;  // sum_{l'<l} (H+1)(W+1)
+    int bin_start;  // first sub-bin of the level
+    int nch_log2;   // log2(sub-bins per bin)
+    int pad[3];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -79,51 +89,57 @@ template <> struct Elem<double> {
     __device__ static double from_f(double v) { return v; }
 };
 
-// 128-bit row fragment load -> fp32 registers (read-only path)
-__device__ __forceinline__ void load_vec(const float* p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+// Row fragment of VEC consecutive channels <-> fp32 registers.  One access per lane:
+// 128 bits (float x4, 16-bit x8) or 64 bits (16-bit x4); loads take the read-only path.
+template <int BYTES> struct Raw;
+template <> struct Raw<16> { using type = uint4; };
+template <> struct Raw<8> { using type = uint2; };
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_row(const T* p, float (&v)[VEC]) {
+    using R = typename Raw<sizeof(T) * VEC>::type;
+    const R t = __ldg(reinterpret_cast<const R*>(p));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&t);
+    if constexpr (sizeof(T) == 4) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
-        v[2 * i] = __uint_as_float(w[i] << 16);
-        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        for (int i = 0; i < VEC; ++i) v[i] = __uint_as_float(w[i]);
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
     }
 }
-__device__ __forceinline__ void load_vec(const __half* p, float (&v)[8]) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-        v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-}
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[8]) {
-    uint4 t;
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_row(T* p, const float (&v)[VEC]) {
+    using R = typename Raw<sizeof(T) * VEC>::type;
+    R t;
     uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+    if constexpr (sizeof(T) == 4) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = t;
-}
-__device__ __forceinline__ void store_vec(__half* p, const float (&v)[8]) {
-    uint4 t;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+        for (int i = 0; i < VEC; ++i) w[i] = __float_as_uint(v[i]);
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int i = 0; i < VEC / 2; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
     }
-    *reinterpret_cast<uint4*>(p) = t;
+    *reinterpret_cast<R*>(p) = t;
 }
 
 // sampling location (x, y) and attention weight loads in the aux dtype
@@ -188,8 +204,13 @@ __device__ __forceinline__ void corner_pixels(const Sample<CT>& s, const Level& 
     pix[3] = (h1 && w1) ? base + lv.W + 1 : -1;
 }
 
+// Sub-bin of a sample of query q whose top-left corner is (h_lo, w_lo).
+__device__ __forceinline__ int sub_bin(const Level& lv, int h_lo, int w_lo, int q) {
+    return lv.bin_start + ((((h_lo + 1) * (lv.W + 1)) + (w_lo + 1)) << lv.nch_log2) + (q & ((1 << lv.nch_log2) - 1));
+}
+
 // Read the level table into shared memory (threads 0..L-1) and prefix the bin starts.
-// Returns sum_l (H+1)(W+1) through sb and sum_l H*W through sq.
+// Returns the number of sub-bins through sb and sum_l H*W through sq.
 __device__ __forceinline__ void load_levels(const Params& p, Level* lv, int* sb, int* sq) {
     if (threadIdx.x < p.L) {
         const int l = threadIdx.x;
@@ -201,8 +222,13 @@ __device__ __forceinline__ void load_levels(const Params& p, Level* lv, int* sb,
     if (threadIdx.x == 0) {
         int b = 0, q = 0;
         for (int l = 0; l < p.L; ++l) {
+            const long long nb = (long long)(lv[l].H + 1) * (lv[l].W + 1);
+            const long long want = ((long long)p.Lq * p.P + kSubBinTarget * nb - 1) / (kSubBinTarget * nb);
+            int k = 0;
+            while ((1LL << k) < want && k < kMaxSubLog2) ++k;
+            lv[l].nch_log2 = k;
             lv[l].bin_start = b;
-            b += (lv[l].H + 1) * (lv[l].W + 1);
+            b += (int)(nb << k);
             q += lv[l].H * lv[l].W;
         }
         *sb = b;

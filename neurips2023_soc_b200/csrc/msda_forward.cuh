@@ -8,39 +8,39 @@
 // Design (tile kernel, the path taken when a value row is 32..256 bytes):
 //   * persistent CTAs walk (frame, head, query-tile) tiles; a tile's queries are spatially
 //     compact (msda_common.cuh: TileMap) so their corner rows are shared through L1;
-//   * per chunk of 16 samples the CTA first turns the tile's sampling locations and
-//     attention weights (read once, coalesced) into sample DESCRIPTORS in shared memory:
-//     four corner row offsets (-1 = corner outside the map) and the four bilinear weights
-//     already multiplied by the attention weight;
-//   * a group of G = row_bytes/16 lanes owns one (query, head) output row; each lane reads
-//     its 16-byte slice of every corner row with one 128-bit read-only load, so a warp
-//     load instruction fetches 32/G complete rows and every fetched byte is used;
+//   * per chunk of 16 samples the CTA turns the tile's sampling locations and attention
+//     weights (read once, coalesced, prefetched one work item ahead) into 16-byte sample
+//     DESCRIPTORS in a shared-memory double buffer (msda_tiles.cuh);
+//   * a group of G lanes owns one (query, head) output row; each lane reads its slice of
+//     every corner row with one vector read-only load (128-bit; 64-bit for 64-byte bf16
+//     rows so that a row is still spread over 8 lanes), so a warp load instruction fetches
+//     32/G complete rows and every fetched byte is used;
 //   * accumulation over the L*P samples is in registers, the output row leaves with one
 //     128-bit store per lane.
 #pragma once
 
-#include "msda_common.cuh"
+#include "msda_tiles.cuh"
 
 namespace msda {
 
-// Shared-memory descriptor arrays for one round: [groups][kDescStride] x 16 B each.
-template <int NG>
-struct FwdSmem {
-    int4 off[NG * kDescStride];
-    float4 wgt[NG * kDescStride];
-};
+#ifndef MSDA_FWD_MIN_BLOCKS
+#define MSDA_FWD_MIN_BLOCKS 3
+#endif
 
-template <typename T, typename TA, int G>
-__global__ void __launch_bounds__(kThreads) msda_fwd_tile_kernel(const Params p, const int rounds) {
-    constexpr int VEC = Elem<T>::kVec;
-    constexpr int NG = kThreads / G;            // (query, head) rows in flight per round
-    constexpr int DPT = NG * kSC / kThreads;    // descriptors each thread builds per chunk
-    static_assert(NG * kSC % kThreads == 0, "descriptor staging must divide evenly");
+// T value dtype, TA location/weight dtype, VEC channels per lane, G = D / VEC lanes per row,
+// P points per level (compile time so that the per-level constants hoist out of the loop).
+template <typename T, typename TA, int VEC, int G, int P>
+__global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_kernel(const Params p, const int rounds) {
+    using TS = TileShape<G>;
+    constexpr int NG = TS::NG;
+    constexpr int LPC = (P >= kSC) ? 1 : kSC / P;   // levels per 16-sample chunk
+    constexpr int PPC = (P >= kSC) ? kSC : P;       // points of one level per chunk
+    static_assert(kSC % PPC == 0 && (P % PPC) == 0, "P must divide or be a multiple of 16");
 
     __shared__ Level lv[kMaxLevels];
     __shared__ TileMap tm;
     __shared__ int s_sb, s_sq;
-    __shared__ FwdSmem<NG> sm;
+    __shared__ uint4 desc[2][NG * kDescStride];
 
     const int tile_q = NG * rounds;
     load_levels(p, lv, &s_sb, &s_sq);
@@ -51,85 +51,78 @@ __global__ void __launch_bounds__(kThreads) msda_fwd_tile_kernel(const Params p,
     const TA* __restrict__ attn = static_cast<const TA*>(p.attn);
     T* __restrict__ out = static_cast<T*>(p.out);
 
-    const int tid = threadIdx.x;
-    const int grp = tid / G, gl = tid % G;
-    const int st_s = tid % kSC;                 // sample slot this thread stages
-    const int st_j0 = tid / kSC;                // first row it stages; then += kThreads/kSC
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
     const int row_elems = p.M * p.D;
     const int total_tiles = p.N * p.M * tm.qtiles;
 
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const Tile tl = decode_tile(p, lv, &tm, t, tile_q);
-        const T* vbase = value + (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
+    Work cur{(int)blockIdx.x, 0, 0};
+    if (cur.t >= total_tiles) return;
+    Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
+    Staged<TS::DPT> st;
+    stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
+    stage_build<G, P, false>(st, p, lv, tl, cur, desc[0]);
+    __syncthreads();
 
-        for (int r = 0; r < rounds; ++r) {
-            float acc[VEC];
+    int buf = 0;
+    float acc[VEC];
+    while (true) {
+        const Work nxt = next_work(cur, rounds, p.LP);
+        const bool has_next = nxt.t < total_tiles;
+        Tile ntl = tl;
+        if (has_next) {
+            if (nxt.t != cur.t) ntl = decode_tile(p, lv, &tm, nxt.t, tile_q);
+            stage_load<TA, G>(st, p, &tm, ntl, nxt, loc, attn);      // HBM loads fly during the gather
+        }
+
+        const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);
+        if (cur.c0 == 0) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-            const int q_mine = tile_query(p, &tm, tl, r * NG + grp);
-
-            for (int c0 = 0; c0 < p.LP; c0 += kSC) {
-                __syncthreads();                // previous chunk's descriptors are consumed
-                // ---- stage: locations + weights -> descriptors ----
-                const int sg = c0 + st_s;       // sample index inside (l, p)
-                const bool s_ok = sg < p.LP;
-                const int l = s_ok ? sg / p.P : 0;
-                const Level L_ = lv[l];
-#pragma unroll
-                for (int k = 0; k < DPT; ++k) {
-                    const int j = st_j0 + k * (kThreads / kSC);
-                    const int q = tile_query(p, &tm, tl, r * NG + j);
-                    int4 o = make_int4(-1, -1, -1, -1);
-                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s_ok && q >= 0) {
-                        const size_t si = (((size_t)tl.n * p.Lq + q) * p.M + tl.m) * p.LP + sg;
-                        const XY<float> xy = load_xy(loc + 2 * si);
-                        const float a = Elem<TA>::to_f(__ldg(attn + si));
-                        const Sample<float> s = locate(xy.x, xy.y, L_.H, L_.W);
-                        if (s.ok) {
-                            int pix[4];
-                            corner_pixels(s, L_, pix);
-                            o.x = pix[0] < 0 ? -1 : pix[0] * row_elems;
-                            o.y = pix[1] < 0 ? -1 : pix[1] * row_elems;
-                            o.z = pix[2] < 0 ? -1 : pix[2] * row_elems;
-                            o.w = pix[3] < 0 ? -1 : pix[3] * row_elems;
-                            const float hh = 1.f - s.lh, hw = 1.f - s.lw;
-                            w.x = hh * hw * a; w.y = hh * s.lw * a;
-                            w.z = s.lh * hw * a; w.w = s.lh * s.lw * a;
-                        }
-                    }
-                    sm.off[j * kDescStride + st_s] = o;
-                    sm.wgt[j * kDescStride + st_s] = w;
-                }
-                __syncthreads();
-                // ---- gather: 4 corner rows per sample, 128 bits per lane ----
-                if (q_mine >= 0) {
-#pragma unroll 4
-                    for (int s = 0; s < kSC; ++s) {
-                        const int4 o = sm.off[grp * kDescStride + s];
-                        const float4 w = sm.wgt[grp * kDescStride + s];
-                        float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                        if (o.x >= 0) load_vec(vbase + o.x, v0);
-                        if (o.y >= 0) load_vec(vbase + o.y, v1);
-                        if (o.z >= 0) load_vec(vbase + o.z, v2);
-                        if (o.w >= 0) load_vec(vbase + o.w, v3);
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            acc[i] = fmaf(w.x, v0[i], acc[i]);
-                            acc[i] = fmaf(w.y, v1[i], acc[i]);
-                            acc[i] = fmaf(w.z, v2[i], acc[i]);
-                            acc[i] = fmaf(w.w, v3[i], acc[i]);
-                        }
-                    }
-                }
-            }
-            if (q_mine >= 0) {
-                T* o = out + (((size_t)tl.n * p.Lq + q_mine) * p.M + tl.m) * p.D + gl * VEC;
-                store_vec(o, acc);
-            }
         }
+        if (q_mine >= 0) {
+            const T* vbase = value + (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
+            const uint4* drow = desc[buf] + grp * kDescStride;
+            const int l0 = cur.c0 / P;
+#pragma unroll 1
+            for (int lc = 0; lc < LPC; ++lc) {
+                const int l = l0 + lc;
+                if (l >= p.L) break;
+                const LevelPitch lp = level_pitch(lv[l], row_elems);
+                const int sbase = (P >= kSC) ? 0 : lc * PPC;
+#pragma unroll
+                for (int pp = 0; pp < PPC; ++pp) {
+                    const uint4 d = drow[sbase + pp];
+                    const T* c0p = vbase + (lp.base + (long long)(d.x & 0x0fffffffu) * row_elems);
+                    const T* c2p = c0p + lp.wrow;
+                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
+                    if (d.x & (1u << 28)) load_row<T, VEC>(c0p, v0);
+                    if (d.x & (2u << 28)) load_row<T, VEC>(c0p + row_elems, v1);
+                    if (d.x & (4u << 28)) load_row<T, VEC>(c2p, v2);
+                    if (d.x & (8u << 28)) load_row<T, VEC>(c2p + row_elems, v3);
+                    const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
+                    const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+                    const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        acc[i] = fmaf(w0, v0[i], acc[i]);
+                        acc[i] = fmaf(w1, v1[i], acc[i]);
+                        acc[i] = fmaf(w2, v2[i], acc[i]);
+                        acc[i] = fmaf(w3, v3[i], acc[i]);
+                    }
+                }
+            }
+            if (cur.c0 + kSC >= p.LP)
+                store_row<T, VEC>(out + (((size_t)tl.n * p.Lq + q_mine) * p.M + tl.m) * p.D + gl * VEC, acc);
+        }
+
+        if (has_next) stage_build<G, P, false>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        __syncthreads();
+        if (!has_next) break;
+        cur = nxt;
+        tl = ntl;
+        buf ^= 1;
     }
 }
 

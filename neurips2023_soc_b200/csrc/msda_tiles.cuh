@@ -1,0 +1,126 @@
+// msda_tiles.cuh -- the software pipeline shared by the forward and the sample-gradient tile
+// kernels: persistent CTAs walk (tile, round, chunk) work items; while the CTA gathers value
+// rows for the current item, the sampling locations / attention weights of the NEXT item
+// are already in flight from HBM (registers), and are turned into 16-byte sample
+// descriptors in the other half of a shared-memory double buffer -- one block barrier per
+// item, no exposed DRAM latency.
+//
+// Sample descriptor (one uint4 per (query, sample), read with a single LDS.128 broadcast):
+//   .x  bits 0..27  rel = (h_lo+1)*W + (w_lo+1)   pixel index of the top-left corner, shifted by
+//                   one row and one column so that it is never negative (cuh:38-45 geometry)
+//       bits 28..31 which of the four corners lie inside the map (cuh:56,62,68,74)
+//   .y  lh   .z  lw   (fractional parts, fp32 bits)      .w  attention weight (fp32 bits)
+// A rejected sample (cuh:288) or an empty slot has no corner bit set and weight 0.
+// The gather derives the four row addresses from rel and the level's row pitch and the four
+// bilinear weights from lh/lw: more ALU, a quarter of the shared-memory traffic of storing
+// them.
+#pragma once
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+struct Work {
+    int t, r, c0;   // tile, round inside the tile, first sample of the chunk
+};
+
+template <int DPT>
+struct Staged {     // what a staging thread carries from prefetch to descriptor build
+    float x[DPT], y[DPT], a[DPT];
+    int q[DPT];     // query index, -1: empty slot
+};
+
+template <int G>
+struct TileShape {
+    static constexpr int NG = kThreads / G;           // (query, head) rows per round
+    static constexpr int DPT = NG * kSC / kThreads;   // descriptors per staging thread
+    static_assert(NG * kSC % kThreads == 0, "descriptor staging must divide evenly");
+};
+
+__device__ __forceinline__ Work next_work(const Work w, const int rounds, const int LP) {
+    Work n = w;
+    n.c0 += kSC;
+    if (n.c0 >= LP) {
+        n.c0 = 0;
+        if (++n.r >= rounds) {
+            n.r = 0;
+            n.t += gridDim.x;
+        }
+    }
+    return n;
+}
+
+// Issue the global loads of one work item (no use of the results here).
+template <typename TA, int G>
+__device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const Params& p, const TileMap* tm,
+                                           const Tile& tl, const Work& w, const TA* __restrict__ loc,
+                                           const TA* __restrict__ attn) {
+    constexpr int NG = TileShape<G>::NG, DPT = TileShape<G>::DPT;
+    const int st_s = threadIdx.x % kSC, st_j0 = threadIdx.x / kSC;
+    const int sg = w.c0 + st_s;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const int j = st_j0 + k * (kThreads / kSC);
+        int q = tile_query(p, tm, tl, w.r * NG + j);
+        if (sg >= p.LP) q = -1;
+        st.q[k] = q;
+        st.x[k] = st.y[k] = st.a[k] = 0.f;
+        if (q >= 0) {
+            const size_t si = (((size_t)tl.n * p.Lq + q) * p.M + tl.m) * p.LP + sg;
+            const XY<float> xy = load_xy(loc + 2 * si);
+            st.x[k] = xy.x; st.y[k] = xy.y;
+            st.a[k] = Elem<TA>::to_f(__ldg(attn + si));
+        }
+    }
+}
+
+// Turn the staged locations into descriptors.  With COUNT the accepted samples also take
+// their slot in the inverse index used by the grad_value gather (msda_backward.cuh, part B).
+template <int G, int P, bool COUNT>
+__device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
+                                            const Tile& tl, const Work& w, uint4* __restrict__ desc) {
+    constexpr int DPT = TileShape<G>::DPT;
+    const int st_s = threadIdx.x % kSC, st_j0 = threadIdx.x / kSC;
+    const int sg = w.c0 + st_s;
+    const int l = min(sg / P, p.L - 1);
+    const Level L_ = lv[l];
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const int j = st_j0 + k * (kThreads / kSC);
+        uint4 d = make_uint4(0u, 0u, 0u, 0u);
+        if (st.q[k] >= 0) {
+            const Sample<float> s = locate(st.x[k], st.y[k], L_.H, L_.W);
+            uint32_t slot = 0xffffffffu;
+            if (s.ok) {
+                const unsigned h0 = s.h_lo >= 0, w0 = s.w_lo >= 0;
+                const unsigned h1 = s.h_lo + 1 <= L_.H - 1, w1 = s.w_lo + 1 <= L_.W - 1;
+                const unsigned flags = (h0 & w0) | ((h0 & w1) << 1) | ((h1 & w0) << 2) | ((h1 & w1) << 3);
+                d.x = (flags << 28) | (unsigned)((s.h_lo + 1) * L_.W + (s.w_lo + 1));
+                d.y = __float_as_uint(s.lh);
+                d.z = __float_as_uint(s.lw);
+                d.w = __float_as_uint(st.a[k]);
+                if constexpr (COUNT)
+                    slot = atomicAdd(p.bin_off + (size_t)(tl.n * p.M + tl.m) * (p.sb_max + 1) +
+                                         sub_bin(L_, s.h_lo, s.w_lo, st.q[k]), 1u);
+            }
+            if constexpr (COUNT)
+                p.pos[(((size_t)tl.n * p.Lq + st.q[k]) * p.M + tl.m) * p.LP + sg] = slot;
+        }
+        desc[j * kDescStride + st_s] = d;
+    }
+}
+
+// per-level constants of the gather
+struct LevelPitch {
+    long long base;   // element offset of the virtual pixel (row -1, col -1) of the level
+    int wrow;         // elements between vertically adjacent pixels
+};
+
+__device__ __forceinline__ LevelPitch level_pitch(const Level& L_, const int row_elems) {
+    LevelPitch lp;
+    lp.base = ((long long)L_.start - L_.W - 1) * row_elems;
+    lp.wrow = L_.W * row_elems;
+    return lp;
+}
+
+}  // namespace msda
