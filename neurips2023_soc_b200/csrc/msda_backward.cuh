@@ -541,15 +541,14 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_big_kernel(const Param
 // into two shared-memory tiles with plain stores -- every element is written exactly once, so
 // there is nothing to zero and nothing to race on.  After one barrier the CTA stores T + B
 // with vector stores.
-// The entries of the bins of one row segment are contiguous in memory (bins are numbered
-// row-major and the scan is over bin index), so the walk is a linear stream: the nine bin
-// boundaries are read up front, entries are fetched G at a time one batch ahead, and the
-// owner lane of an entry forms its four weight products and its bin once for the group.
+// The entries of a bin (all its sub-bins) are contiguous and sorted; bin boundaries are read
+// one bin ahead and entries one batch ahead (G at a time, one per lane; the owner lane forms
+// the entry's four weight products once for the group), so that only the grad_output row
+// loads of a batch are exposed.  All groups of a warp run the same bin loop.
 // In dense levels (many entries per bin) the 32/G groups of a warp share each bin -- each takes
 // a contiguous share of its entries -- and combine their sums with shuffles in a fixed order.
 constexpr int kGThreads = 128;
 constexpr int kGTileW = 8;
-constexpr int kGBounds = kGTileW + 2;   // boundaries of the up to 9 bins of a row segment
 
 template <int VEC>
 struct BinAcc {
@@ -637,11 +636,16 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
             float* const tdst = sT + (row - 1) * TW * D + gl * VEC;
             float* const bdst = sB + row * TW * D + gl * VEC;
 
-            // entry offsets at the boundaries of the row segment's bins
+            // Entry offsets at the bin boundaries of the row segment, read one bin ahead.
             const uint32_t* orow = off + L_.bin_start + ((by * (L_.W + 1) + x0) << L_.nch_log2);
-            uint32_t bb[kGBounds];
-#pragma unroll
-            for (int j = 0; j < kGBounds; ++j) bb[j] = orow[(j <= nb ? j : nb) << L_.nch_log2];
+            auto bound = [&](const int j) { return orow[min(j, nb) << L_.nch_log2]; };
+            // the share of bin [lo, hi) this group works on: all of it, or 1/GW of it in dense levels
+            auto share = [&](const uint32_t lo, const uint32_t hi, uint32_t& r0, uint32_t& r1) {
+                if (!dense) { r0 = lo; r1 = hi; return; }
+                const uint32_t len = (hi - lo + GW - 1) / GW;
+                r0 = min(hi, lo + gw * len);
+                r1 = min(hi, r0 + len);
+            };
 
             BinAcc<VEC> acc;
             acc.clear();
@@ -649,8 +653,68 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
 #pragma unroll
             for (int i = 0; i < VEC; ++i) p2[i] = p4[i] = 0.f;
 
-            // finish bin `b`: emit the pixel to its left, hand G2/G4 on, start the next bin
-            auto emit = [&](const int b) {
+            uint32_t b_lo = bound(0), b_hi = bound(1), b_nx = bound(2);
+            uint32_t r0, r1, n0, n1;
+            share(b_lo, b_hi, r0, r1);
+            share(b_hi, b_nx, n0, n1);
+            Entry<float> nxt = load_entry(ent, r0 + gl, r1);
+
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                const uint32_t b_nn = bound(b + 3);                 // boundary needed two bins from now
+                uint32_t e0 = r0;
+                while (true) {
+                    const Entry<float> mine = nxt;
+                    const bool more = e0 + G < r1;
+                    nxt = more ? load_entry(ent, e0 + G + gl, r1) : load_entry(ent, n0 + gl, n1);
+                    const int nbat = e0 < r1 ? (int)min((uint32_t)G, r1 - e0) : 0;
+                    const float ah = mine.a * (1.f - mine.lh), al = mine.a * mine.lh, hw = 1.f - mine.lw;
+                    const float myw[4] = {ah * hw, ah * mine.lw, al * hw, al * mine.lw};
+                    const uint32_t myq = mine.id >> p.id_shift;
+#pragma unroll
+                    for (int c0 = 0; c0 < G; c0 += STEP) {
+                        if (c0 >= nbat) break;
+                        float gv[STEP][VEC];
+#pragma unroll
+                        for (int e = 0; e < STEP; ++e) {
+                            const uint32_t q = __shfl_sync(gmask, myq, c0 + e, G);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) gv[e][i] = 0.f;
+                            if (c0 + e < nbat) load_row<T, VEC>(gbase + (size_t)q * qstride, gv[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < STEP; ++e) {
+                            // entries past nbat carry zero weights and zero rows
+                            const float w0 = __shfl_sync(gmask, myw[0], c0 + e, G);
+                            const float w1 = __shfl_sync(gmask, myw[1], c0 + e, G);
+                            const float w2 = __shfl_sync(gmask, myw[2], c0 + e, G);
+                            const float w3 = __shfl_sync(gmask, myw[3], c0 + e, G);
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) {
+                                acc.g1[i] = fmaf(w0, gv[e][i], acc.g1[i]);
+                                acc.g2[i] = fmaf(w1, gv[e][i], acc.g2[i]);
+                                acc.g3[i] = fmaf(w2, gv[e][i], acc.g3[i]);
+                                acc.g4[i] = fmaf(w3, gv[e][i], acc.g4[i]);
+                            }
+                        }
+                    }
+                    if (!more) break;
+                    e0 += G;
+                }
+                if (dense) {
+                    // fixed-order combine over the GW groups of the warp (lane bits >= log2 G)
+#pragma unroll
+                    for (int d = G; d < 32; d <<= 1) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            acc.g1[i] += __shfl_xor_sync(0xffffffffu, acc.g1[i], d);
+                            acc.g2[i] += __shfl_xor_sync(0xffffffffu, acc.g2[i], d);
+                            acc.g3[i] += __shfl_xor_sync(0xffffffffu, acc.g3[i], d);
+                            acc.g4[i] += __shfl_xor_sync(0xffffffffu, acc.g4[i], d);
+                        }
+                    }
+                }
+                // finish the bin: the pixel to its left is complete; hand G2/G4 on
                 if (b > 0 && (!dense || gw == 0)) {
                     if (emit_t) {
 #pragma unroll
@@ -664,86 +728,9 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) { p2[i] = acc.g2[i]; p4[i] = acc.g4[i]; }
                 acc.clear();
-            };
-
-            // stream entries [e_beg, e_end): `tagged` entries carry their bin, bins are emitted on change
-            auto stream = [&](const uint32_t e_beg, const uint32_t e_end, int& cur_bin, const bool tagged) {
-                Entry<float> nxt = load_entry(ent, e_beg + gl, e_end);
-                for (uint32_t e0 = e_beg; e0 < e_end; e0 += G) {
-                    const Entry<float> mine = nxt;
-                    nxt = load_entry(ent, e0 + G + gl, e_end);
-                    const int nbat = (int)min((uint32_t)G, e_end - e0);
-                    const float ah = mine.a * (1.f - mine.lh), al = mine.a * mine.lh, hw = 1.f - mine.lw;
-                    const float myw[4] = {ah * hw, ah * mine.lw, al * hw, al * mine.lw};
-                    const uint32_t myq = mine.id >> p.id_shift;
-                    int mybin = 0;
-                    if (tagged) {
-                        const uint32_t pos = e0 + gl;
-#pragma unroll
-                        for (int j = 1; j < kGBounds - 1; ++j) mybin += (j < nb && bb[j] <= pos);
-                    }
-#pragma unroll
-                    for (int c0 = 0; c0 < G; c0 += STEP) {
-                        if (c0 >= nbat) break;
-                        float gv[STEP][VEC], w[STEP][4];
-                        int bin[STEP];
-#pragma unroll
-                        for (int e = 0; e < STEP; ++e) {
-                            const uint32_t q = __shfl_sync(gmask, myq, c0 + e, G);
-                            bin[e] = __shfl_sync(gmask, mybin, c0 + e, G);
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) w[e][kk] = __shfl_sync(gmask, myw[kk], c0 + e, G);
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) gv[e][i] = 0.f;
-                            if (c0 + e < nbat) load_row<T, VEC>(gbase + (size_t)q * qstride, gv[e]);
-                        }
-#pragma unroll
-                        for (int e = 0; e < STEP; ++e) {
-                            if (c0 + e < nbat) {
-                                if (tagged) {
-                                    while (cur_bin < bin[e]) emit(cur_bin++);
-                                }
-#pragma unroll
-                                for (int i = 0; i < VEC; ++i) {
-                                    acc.g1[i] = fmaf(w[e][0], gv[e][i], acc.g1[i]);
-                                    acc.g2[i] = fmaf(w[e][1], gv[e][i], acc.g2[i]);
-                                    acc.g3[i] = fmaf(w[e][2], gv[e][i], acc.g3[i]);
-                                    acc.g4[i] = fmaf(w[e][3], gv[e][i], acc.g4[i]);
-                                }
-                            }
-                        }
-                    }
-                }
-            };
-
-            if (!dense) {
-                int cur_bin = 0;
-                stream(bb[0], bb[kGBounds - 1], cur_bin, true);      // bb[last] == bb[nb]
-                while (cur_bin < nb) emit(cur_bin++);
-            } else {
-#pragma unroll 1
-                for (int b = 0; b < nb; ++b) {
-                    uint32_t b0 = bb[0], b1 = bb[1];
-#pragma unroll
-                    for (int j = 1; j < kGBounds - 1; ++j)
-                        if (j == b) { b0 = bb[j]; b1 = bb[j + 1]; }
-                    const uint32_t share = (b1 - b0 + GW - 1) / GW;
-                    const uint32_t r0 = min(b1, b0 + gw * share), r1 = min(b1, r0 + share);
-                    int unused = 0;
-                    stream(r0, r1, unused, false);
-                    // fixed-order combine over the GW groups of the warp (lane bits >= log2 G)
-#pragma unroll
-                    for (int d = G; d < 32; d <<= 1) {
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) {
-                            acc.g1[i] += __shfl_xor_sync(0xffffffffu, acc.g1[i], d);
-                            acc.g2[i] += __shfl_xor_sync(0xffffffffu, acc.g2[i], d);
-                            acc.g3[i] += __shfl_xor_sync(0xffffffffu, acc.g3[i], d);
-                            acc.g4[i] += __shfl_xor_sync(0xffffffffu, acc.g4[i], d);
-                        }
-                    }
-                    emit(b);
-                }
+                b_lo = b_hi; b_hi = b_nx; b_nx = b_nn;
+                r0 = n0; r1 = n1;
+                share(b_hi, b_nx, n0, n1);
             }
         }
         __syncthreads();
