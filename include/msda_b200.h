@@ -120,6 +120,14 @@ int msda_backward_ex(const void *value, const int64_t *spatial_shapes, const int
  * (bench.py's gpu_launches is counted from this, not guessed). */
 int msda_last_launch_count(void);
 
+/* Per-kernel device timing for benchmarks: when enabled (thread-local), every kernel the
+ * library launches is bracketed by CUDA events on the launching stream.  msda_profile_read
+ * waits for the recorded events, writes up to `cap` durations in milliseconds to `ms` and the
+ * kernel names, newline separated, to `names`; returns the number of records.  Enabling or
+ * disabling clears the records.  Not for production use (two event records per launch). */
+void msda_profile_enable(int on);
+int msda_profile_read(char *names, size_t names_cap, float *ms, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ FLAG_LINEAR_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC8 = 1, 2, 
 EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",
     "msda_backward_workspace_bytes", "msda_backward", "msda_backward_ex", "msda_last_launch_count",
+    "msda_profile_enable", "msda_profile_read",
 )
 
 _lib = None
@@ -47,6 +48,10 @@ def load() -> ctypes.CDLL:
     lib.msda_backward.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp]
     lib.msda_backward_ex.restype = i
     lib.msda_backward_ex.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp, u]
+    lib.msda_profile_enable.restype = None
+    lib.msda_profile_enable.argtypes = [i]
+    lib.msda_profile_read.restype = i
+    lib.msda_profile_read.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(ctypes.c_float), i]
     _lib = lib
     return lib
 
@@ -55,3 +60,16 @@ def check(status: int) -> None:
     if status != 0:
         msg = load().msda_last_error().decode("utf-8", "replace")
         raise MSDAError(f"libmsda_b200 status {status}: {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    load().msda_profile_enable(1 if on else 0)
+
+
+def profile_read(cap: int = 4096):
+    """[(kernel name, milliseconds)] recorded since profile_enable(True)."""
+    names = ctypes.create_string_buffer(64 * cap)
+    ms = (ctypes.c_float * cap)()
+    n = load().msda_profile_read(names, len(names), ms, cap)
+    labels = names.value.decode().split("\n")[:n]
+    return list(zip(labels, [float(ms[k]) for k in range(n)]))

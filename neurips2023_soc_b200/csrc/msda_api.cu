@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/msda_b200.h"
@@ -22,6 +23,27 @@ using namespace msda;
 
 thread_local std::string g_error;
 thread_local int g_launches = 0;
+
+// Optional per-kernel timing (bench.py's roofline leg): when enabled, every launch is bracketed
+// by CUDA events on the launching stream; msda_profile_read() turns them into milliseconds.
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+thread_local bool g_prof = false;
+thread_local std::vector<ProfRec> g_recs;
+
+void prof_begin(cudaStream_t st, const char* name) {
+    if (!g_prof) return;
+    ProfRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    if (g_prof && !g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -169,7 +191,9 @@ int launch_fwd_tile(const Params& p, cudaStream_t st) {
     const int tile_q = (kThreads / G) * rounds;
     auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P>;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
+    prof_begin(st, "msda_fwd_tile_kernel");
     k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+    prof_end(st);
     MSDA_LAUNCHED("msda_fwd_tile_kernel");
     return MSDA_OK;
 }
@@ -179,7 +203,9 @@ int launch_fwd_generic(const Params& p, cudaStream_t st) {
     auto k = msda_fwd_generic_kernel<T, TA, CT>;
     const long long blocks = ceil_div((long long)p.N * p.Lq * p.M * p.D, kThreads);
     const long long cap = (long long)num_sms() * 16;
+    prof_begin(st, "msda_fwd_generic_kernel");
     k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_fwd_generic_kernel");
     return MSDA_OK;
 }
@@ -194,13 +220,17 @@ int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
     if constexpr (std::is_same<T, float>::value) {
         if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) {
             auto ka = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, false, true>;
+            prof_begin(st, "msda_bwd_sample_tile_kernel<atomic>");
             ka<<<persistent_grid(ka, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+            prof_end(st);
             MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<atomic>");
             return MSDA_OK;
         }
     }
     auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false>;
+    prof_begin(st, "msda_bwd_sample_tile_kernel");
     k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+    prof_end(st);
     MSDA_LAUNCHED("msda_bwd_sample_tile_kernel");
     return MSDA_OK;
 }
@@ -210,7 +240,9 @@ int launch_bwd_sample_generic(const Params& p, cudaStream_t st) {
     auto k = msda_bwd_sample_generic_kernel<T, TA, CT>;
     const long long blocks = ceil_div((long long)p.N * p.Lq * p.M, kThreads / 32);
     const long long cap = (long long)num_sms() * 8;
+    prof_begin(st, "msda_bwd_sample_generic_kernel");
     k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_bwd_sample_generic_kernel");
     return MSDA_OK;
 }
@@ -227,21 +259,31 @@ int launch_binning(const Params& p, bool counted, cudaStream_t st) {
     const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
     const int egrid = elementwise_grid(samples);
     if (!counted) {
+        prof_begin(st, "msda_bin_count_kernel");
         msda_bin_count_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+        prof_end(st);
         MSDA_LAUNCHED("msda_bin_count_kernel");
     }
+    prof_begin(st, "msda_bin_scan_kernel");
     msda_bin_scan_kernel<<<p.N * p.M, 1024, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_bin_scan_kernel");
+    prof_begin(st, "msda_bin_fill_kernel");
     msda_bin_fill_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_bin_fill_kernel");
     {
         const long long spans = (long long)p.N * p.M * ceil_div(p.sb_max, 32);
         const long long sb = ceil_div(spans, kThreads / 32);
         const long long scap = (long long)num_sms() * 8;
+        prof_begin(st, "msda_bin_sort_small_kernel");
         msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
+        prof_end(st);
         MSDA_LAUNCHED("msda_bin_sort_small_kernel");
     }
+    prof_begin(st, "msda_bin_sort_big_kernel");
     msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_bin_sort_big_kernel");
     return MSDA_OK;
 }
@@ -251,7 +293,9 @@ int launch_grad_value_walk(const Params& p, cudaStream_t st) {
     auto k = msda_grad_value_walk_kernel<T, VEC, G>;
     // tiles per (frame, head) are only known on the device; S / 8 bounds them from above
     const long long tiles = (long long)p.N * p.M * (p.S / 8 + p.L);
+    prof_begin(st, "msda_grad_value_walk_kernel");
     k<<<persistent_grid(k, kGThreads, tiles), kGThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_grad_value_walk_kernel");
     return MSDA_OK;
 }
@@ -261,7 +305,9 @@ int launch_grad_value_generic(const Params& p, cudaStream_t st) {
     auto k = msda_grad_value_generic_kernel<T, CT>;
     const long long blocks = ceil_div((long long)p.N * p.S * p.M, kThreads / 32);
     const long long cap = (long long)num_sms() * 8;
+    prof_begin(st, "msda_grad_value_generic_kernel");
     k<<<(int)(blocks < cap ? blocks : cap), kThreads, 0, st>>>(p);
+    prof_end(st);
     MSDA_LAUNCHED("msda_grad_value_generic_kernel");
     return MSDA_OK;
 }
@@ -380,6 +426,36 @@ const char* msda_last_error(void) { return g_error.c_str(); }
 
 int msda_last_launch_count(void) { return g_launches; }
 
+void msda_profile_enable(int on) {
+    for (auto& r : g_recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_recs.clear();
+    g_prof = on != 0;
+}
+
+int msda_profile_read(char* names, size_t names_cap, float* ms, int cap) {
+    int n = 0;
+    size_t used = 0;
+    if (names && names_cap) names[0] = 0;
+    for (auto& r : g_recs) {
+        if (n >= cap) break;
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = -1.f;
+        ms[n] = t;
+        const size_t len = strlen(r.name);
+        if (names && used + len + 2 <= names_cap) {
+            memcpy(names + used, r.name, len);
+            names[used + len] = '\n';
+            names[used + len + 1] = 0;
+            used += len + 1;
+        }
+        ++n;
+    }
+    return n;
+}
+
 int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                     const void* sampling_loc, const void* attn_weight, void* output, int N, int S, int M,
                     int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
@@ -480,7 +556,9 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
         p.big_bins = reinterpret_cast<uint32_t*>(base + w.big);
         p.pos = reinterpret_cast<uint32_t*>(base + w.pos);
         p.entries = base + w.entries;
+        prof_begin(st, "memset(bin table)");
         MSDA_CUDA(cudaMemsetAsync(base + w.bin_off, 0, w.counts + 4 * sizeof(uint32_t), st));
+        prof_end(st);
         ++g_launches;
     } else {
         MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)N * S * M * D * dtype_size(value_dtype), st));

@@ -22,7 +22,7 @@ def lib():
 
 def test_header_symbols_are_exported(lib):
     header = (ROOT / "include" / "msda_b200.h").read_text()
-    declared = set(re.findall(r"^\s*(?:int|size_t|const char \*)\s*\*?\s*(msda_\w+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^\s*(?:int|void|size_t|const char \*)\s*\*?\s*(msda_\w+)\s*\(", header, re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/msda_b200.h but not exported"
