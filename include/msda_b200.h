@@ -76,7 +76,7 @@ enum msda_status {
 };
 
 /* flags for msda_*_ex: tuning / A-B switches, never needed for correctness */
-#define MSDA_FLAG_LINEAR_TILES 1u  /* do not assume queries are pyramid pixels when Lq == S */
+#define MSDA_FLAG_PYRAMID_TILES 1u /* A/B: 8x16 pixel query tiles when the queries are the pyramid's pixels */
 #define MSDA_FLAG_GENERIC 2u       /* force the any-D scalar kernels */
 #define MSDA_FLAG_ATOMIC_GRAD_VALUE 4u /* bench-only: fp32 red.global scatter (NOT deterministic) */
 #define MSDA_FLAG_BF16_VEC8 8u     /* A/B: 64-byte bf16 rows on 4 lanes x 128 bit instead of 8 x 64 bit */

@@ -5,11 +5,14 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmsda_b200.so"
+# MSDA_LIB selects another build of the same library (kernel-variant A/B runs in tools/)
+LIB_PATH = Path(os.environ["MSDA_LIB"]) if os.environ.get("MSDA_LIB") else PKG / "libmsda_b200.so"
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
-FLAG_LINEAR_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC8 = 1, 2, 4, 8
+FLAG_PYRAMID_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC8 = 1, 2, 4, 8
 
 EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",

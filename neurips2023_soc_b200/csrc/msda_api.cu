@@ -479,6 +479,7 @@ int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int6
     if (pl.tile && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight)))
         pl.tile = false;
     if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;   // descriptor holds a 28-bit pixel index
+    if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 32)) pl.tile = false;  // 32-bit byte offsets
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {

@@ -70,11 +70,11 @@ __device__ __forceinline__ void exchange_halve(float* v, const bool upper) {
     }
 }
 
-template <int G>
+template <int G, int NV>
 __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
-    // v holds 4*kSC partials; afterwards v[0 .. 4*kSC/G) are complete sums for
-    // indices [gl*4*kSC/G, (gl+1)*4*kSC/G).
-    constexpr int NV = 4 * kSC;
+    // v holds NV partials per lane; afterwards v[0 .. NV/G) are complete sums for
+    // indices [gl*NV/G, (gl+1)*NV/G).
+    static_assert(NV % G == 0, "every lane must end up with a whole number of values");
     if constexpr (G >= 16) exchange_halve<NV * 8 / G, 8>(v, gl & 8);
     if constexpr (G >= 8) exchange_halve<NV * 4 / G, 4>(v, gl & 4);
     if constexpr (G >= 4) exchange_halve<NV * 2 / G, 2>(v, gl & 2);
@@ -82,7 +82,7 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
 }
 
 #ifndef MSDA_BWD_MIN_BLOCKS
-#define MSDA_BWD_MIN_BLOCKS 2
+#define MSDA_BWD_MIN_BLOCKS 3
 #endif
 
 // COUNT: the staging threads also take each accepted sample's slot in the inverse index of
@@ -92,10 +92,8 @@ template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool ATOMI
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
-    constexpr int NSL = kSC / G;               // finished samples per lane after the reduction
     constexpr int LPC = (P >= kSC) ? 1 : kSC / P;
     constexpr int PPC = (P >= kSC) ? kSC : P;
-    static_assert(G <= kSC, "a lane must end up with at least one whole sample");
     static_assert(!ATOMIC || (VEC == 4 && sizeof(T) == 4), "atomic arm is fp32 only");
 
     __shared__ Level lv[kMaxLevels];
@@ -144,32 +142,41 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
             for (int i = 0; i < VEC; ++i) g[i] = 0.f;
             if (q_mine >= 0) load_row<T, VEC>(gout + qm_mine * p.D + gl * VEC, g);
         }
-        const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
-        const T* vbase = value + frame_off;
+        const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D;
+        const char* fb = reinterpret_cast<const char*>(value) + frame_off * sizeof(T);
+        asm volatile("" : "+l"(fb));         // keep the base in registers (ptxas would re-read it per load)
+        const uint32_t rowb = (uint32_t)row_elems * (uint32_t)sizeof(T);
+        const uint32_t lane_off = (uint32_t)(gl * VEC * sizeof(T));
         const uint4* drow = desc[buf] + grp * kDescStride;
         const int l0 = cur.c0 / P;
 
-        // per-lane partial corner dot products d_k = <g, v_k> for the chunk's 16 samples
-        float part[4 * kSC];
-#pragma unroll
+        // One level (PPC samples) at a time: per-lane partial corner dot products d_k = <g, v_k>,
+        // reduced across the G lanes by a halving exchange, then finished by the lanes that hold them.
+        constexpr int NV = 4 * PPC;                  // partials per lane and level step
+        constexpr int CPL = NV / G;                  // finished corner sums per lane
+        constexpr int LPS = CPL >= 4 ? 1 : 4 / CPL;  // lanes that share one sample afterwards
+        constexpr int SPL = CPL >= 4 ? CPL / 4 : 1;  // samples per lane afterwards
+        static_assert(NV % G == 0 && (CPL >= 4 ? CPL % 4 == 0 : 4 % CPL == 0), "unsupported G / P combination");
+#pragma unroll 1
         for (int lc = 0; lc < LPC; ++lc) {
-            const int l = min(l0 + lc, p.L - 1);          // slots past L*P carry no corner bits
-            const LevelPitch lp = level_pitch(lv[l], row_elems);
+            const int l = l0 + lc;
+            if (l >= p.L) break;                         // uniform: slots past L*P carry nothing
+            const Level& L_ = lv[l];
+            const LevelPitch lp = level_pitch(L_, rowb, lane_off);
             const int sbase = (P >= kSC) ? 0 : lc * PPC;
+            float part[NV];
 #pragma unroll
             for (int pp = 0; pp < PPC; ++pp) {
-                const int s = sbase + pp;
-                const uint4 d = drow[s];
-                const long long o0 = lp.base + (long long)(d.x & 0x0fffffffu) * row_elems;
-                const T* c0p = vbase + o0;
-                const T* c2p = c0p + lp.wrow;
+                const uint4 d = drow[sbase + pp];
+                const uint32_t o0 = lp.base + (d.x & 0x0fffffffu) * rowb;
+                const uint32_t o2 = o0 + lp.wrow;
                 float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                if (d.x & (1u << 28)) load_row<T, VEC>(c0p, v0);
-                if (d.x & (2u << 28)) load_row<T, VEC>(c0p + row_elems, v1);
-                if (d.x & (4u << 28)) load_row<T, VEC>(c2p, v2);
-                if (d.x & (8u << 28)) load_row<T, VEC>(c2p + row_elems, v3);
+                if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o0), v0);
+                if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o0 + rowb)), v1);
+                if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o2), v2);
+                if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o2 + rowb)), v3);
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
@@ -178,39 +185,60 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                     d2 = fmaf(g[i], v2[i], d2);
                     d3 = fmaf(g[i], v3[i], d3);
                 }
-                part[4 * s + 0] = d0; part[4 * s + 1] = d1;
-                part[4 * s + 2] = d2; part[4 * s + 3] = d3;
+                part[4 * pp + 0] = d0; part[4 * pp + 1] = d1;
+                part[4 * pp + 2] = d2; part[4 * pp + 3] = d3;
                 if constexpr (ATOMIC) {
                     const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
                     const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
                     const float w[4] = {ah * hw, ah * lw, al * hw, al * lw};
-                    float* gv = static_cast<float*>(p.grad_value) + frame_off + o0;
-                    const long long oo[4] = {0, row_elems, lp.wrow, (long long)lp.wrow + row_elems};
+                    char* gvb = reinterpret_cast<char*>(p.grad_value) + frame_off * sizeof(T);
+                    const uint32_t oo[4] = {o0, o0 + rowb, o2, o2 + rowb};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((d.x >> (28 + k)) & 1u)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gv + oo[k]),
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gvb + oo[k]),
                                          "f"(w[k] * g[0]), "f"(w[k] * g[1]), "f"(w[k] * g[2]), "f"(w[k] * g[3])
                                          : "memory");
                 }
             }
-        }
-        reduce_scatter<G>(part, gl);
+            reduce_scatter<G, NV>(part, gl);
 
-        if (q_mine >= 0) {
+            // lane gl now holds the complete corner sums with indices [gl*CPL, gl*CPL + CPL)
 #pragma unroll
-            for (int i = 0; i < NSL; ++i) {
-                const int s = gl * NSL + i;
-                const int sgo = cur.c0 + s;
-                if (sgo < p.LP) {
-                    const uint4 d = drow[s];
-                    const Level& L_ = lv[sgo / P];
-                    const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
-                    const float hh = 1.f - lh, hw = 1.f - lw;
-                    const float d0 = part[4 * i], d1 = part[4 * i + 1], d2 = part[4 * i + 2], d3 = part[4 * i + 3];
-                    const float ga = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
-                    const float gx = hh * (d1 - d0) + lh * (d3 - d2);
-                    const float gy = hw * (d2 - d0) + lw * (d3 - d1);
+            for (int i = 0; i < SPL; ++i) {
+                const int s = (gl * CPL) / 4 + i;            // sample inside this level step
+                const int k0 = (gl * CPL) & 3;               // first corner this lane holds (0 unless LPS > 1)
+                const uint4 d = drow[sbase + s];
+                const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                // contribution of corner k to (grad_attn, dX, dY): coefficients (cuh:116-158)
+                const float ca[4] = {hh * hw, hh * lw, lh * hw, lh * lw};
+                const float cx[4] = {-hh, hh, -lh, lh};
+                const float cy[4] = {-hw, -lw, hw, lw};
+                float ga = 0.f, gx = 0.f, gy = 0.f;
+#pragma unroll
+                for (int j = 0; j < (CPL < 4 ? CPL : 4); ++j) {
+                    const float dv = part[4 * i + j];
+                    float fa = ca[j], fx = cx[j], fy = cy[j];
+                    if constexpr (LPS > 1) {                 // k0 + j picks the coefficient at run time
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k0 + j == k) { fa = ca[k]; fx = cx[k]; fy = cy[k]; }
+                    }
+                    ga = fmaf(fa, dv, ga);
+                    gx = fmaf(fx, dv, gx);
+                    gy = fmaf(fy, dv, gy);
+                }
+                if constexpr (LPS > 1) {
+#pragma unroll
+                    for (int dd = 1; dd < LPS; dd <<= 1) {
+                        ga += __shfl_xor_sync(0xffffffffu, ga, dd);
+                        gx += __shfl_xor_sync(0xffffffffu, gx, dd);
+                        gy += __shfl_xor_sync(0xffffffffu, gy, dd);
+                    }
+                }
+                const int sgo = cur.c0 + sbase + s;
+                if (q_mine >= 0 && k0 == 0 && sgo < p.LP) {
                     const size_t si = qm_mine * p.LP + sgo;
                     gattn[si] = Elem<TA>::from_f(ga);
                     gloc[2 * si] = Elem<TA>::from_f((float)L_.W * a * gx);

@@ -239,11 +239,13 @@ __device__ __forceinline__ void load_levels(const Params& p, Level* lv, int* sb,
 
 // ---------------------------------------------------------------------------------------
 // Query tiles.  A tile is a set of up to kTileQ queries of one (frame, head) handled by
-// one CTA pass.  When the queries are the pyramid's own pixels (encoder self-attention:
-// Lq == sum_l H_l*W_l, /root/reference/models/deformable_transformer.py:273-285) a tile
-// is a kTileH x kTileW pixel block of one level, so that the samples of the tile's
-// queries fall into a compact window of every level and hit in L1.  Otherwise a tile
-// is kTileQ consecutive queries.  The choice only affects locality, never results.
+// one CTA pass: kTileQ consecutive queries (for encoder self-attention, where the queries
+// are the pyramid's own pixels, that is 1.6 image rows of the finest level -- already
+// compact enough for L1).  MSDA_FLAG_PYRAMID_TILES switches to kTileH x kTileW pixel
+// blocks of one level when Lq == sum_l H_l*W_l
+// (/root/reference/models/deformable_transformer.py:273-285); measured slower on B200
+// (partial tiles at the coarse levels idle 10 % of the lanes, L1 hit rate is the same), kept
+// as an A/B switch.  The choice only affects locality, never results.
 struct TileMap {
     int pyramid;          // 1: 2-D tiles per level, 0: linear
     int qtiles;           // tiles per (frame, head)
@@ -253,7 +255,7 @@ struct TileMap {
 
 __device__ __forceinline__ void build_tile_map(const Params& p, const Level* lv, int sq, int tile_q, TileMap* tm) {
     if (threadIdx.x == 0) {
-        const bool pyr = (sq == p.Lq) && !(p.flags & 1u) && tile_q == kTileQ;
+        const bool pyr = (sq == p.Lq) && (p.flags & 1u) && tile_q == kTileQ;
         tm->pyramid = pyr;
         if (pyr) {
             int t = 0, q = 0;

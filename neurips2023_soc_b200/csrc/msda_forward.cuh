@@ -24,7 +24,10 @@
 namespace msda {
 
 #ifndef MSDA_FWD_MIN_BLOCKS
-#define MSDA_FWD_MIN_BLOCKS 3
+#define MSDA_FWD_MIN_BLOCKS 4
+#endif
+#ifndef MSDA_FWD_STALE
+#define MSDA_FWD_STALE 0   // 1: corner registers are zeroed once per row instead of once per sample
 #endif
 
 // T value dtype, TA location/weight dtype, VEC channels per lane, G = D / VEC lanes per row,
@@ -65,6 +68,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
 
     int buf = 0;
     float acc[VEC];
+    float v[PPC][4][VEC];      // corner rows in flight; zeroed once per output row (see the weights below)
     while (true) {
         const Work nxt = next_work(cur, rounds, p.LP);
         const bool has_next = nxt.t < total_tiles;
@@ -78,38 +82,61 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
         if (cur.c0 == 0) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int a = 0; a < PPC; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) v[a][b][i] = 0.f;
         }
         if (q_mine >= 0) {
-            const T* vbase = value + (size_t)tl.n * p.S * row_elems + tl.m * p.D + gl * VEC;
+            // all addresses of a tile are 32-bit byte offsets from one CTA-uniform base
+            const char* fb = reinterpret_cast<const char*>(value) +
+                             ((size_t)tl.n * p.S * row_elems + tl.m * p.D) * sizeof(T);
+            asm volatile("" : "+l"(fb));     // keep the base in registers (ptxas would re-read it per load)
+            const uint32_t rowb = (uint32_t)row_elems * (uint32_t)sizeof(T);
+            const uint32_t lane_off = (uint32_t)(gl * VEC * sizeof(T));
             const uint4* drow = desc[buf] + grp * kDescStride;
             const int l0 = cur.c0 / P;
 #pragma unroll 1
             for (int lc = 0; lc < LPC; ++lc) {
                 const int l = l0 + lc;
                 if (l >= p.L) break;
-                const LevelPitch lp = level_pitch(lv[l], row_elems);
+                const LevelPitch lp = level_pitch(lv[l], rowb, lane_off);
                 const int sbase = (P >= kSC) ? 0 : lc * PPC;
 #pragma unroll
                 for (int pp = 0; pp < PPC; ++pp) {
                     const uint4 d = drow[sbase + pp];
-                    const T* c0p = vbase + (lp.base + (long long)(d.x & 0x0fffffffu) * row_elems);
-                    const T* c2p = c0p + lp.wrow;
-                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+                    const uint32_t o0 = lp.base + (d.x & 0x0fffffffu) * rowb;
+                    const uint32_t o2 = o0 + lp.wrow;
+#if !MSDA_FWD_STALE
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                    if (d.x & (1u << 28)) load_row<T, VEC>(c0p, v0);
-                    if (d.x & (2u << 28)) load_row<T, VEC>(c0p + row_elems, v1);
-                    if (d.x & (4u << 28)) load_row<T, VEC>(c2p, v2);
-                    if (d.x & (8u << 28)) load_row<T, VEC>(c2p + row_elems, v3);
+                    for (int b = 0; b < 4; ++b)
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) v[pp][b][i] = 0.f;
+#endif
+                    if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o0), v[pp][0]);
+                    if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o0 + rowb)), v[pp][1]);
+                    if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o2), v[pp][2]);
+                    if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o2 + rowb)), v[pp][3]);
                     const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
                     const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+                    // a corner outside the map keeps whatever its registers held (a finite value of this
+                    // row, or the row is NaN already) and gets an exactly zero weight
+#if MSDA_FWD_STALE
+                    const float w0 = (d.x & (1u << 28)) ? ah * hw : 0.f;
+                    const float w1 = (d.x & (2u << 28)) ? ah * lw : 0.f;
+                    const float w2 = (d.x & (4u << 28)) ? al * hw : 0.f;
+                    const float w3 = (d.x & (8u << 28)) ? al * lw : 0.f;
+#else
                     const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+#endif
 #pragma unroll
                     for (int i = 0; i < VEC; ++i) {
-                        acc[i] = fmaf(w0, v0[i], acc[i]);
-                        acc[i] = fmaf(w1, v1[i], acc[i]);
-                        acc[i] = fmaf(w2, v2[i], acc[i]);
-                        acc[i] = fmaf(w3, v3[i], acc[i]);
+                        acc[i] = fmaf(w0, v[pp][0][i], acc[i]);
+                        acc[i] = fmaf(w1, v[pp][1][i], acc[i]);
+                        acc[i] = fmaf(w2, v[pp][2][i], acc[i]);
+                        acc[i] = fmaf(w3, v[pp][3][i], acc[i]);
                     }
                 }
             }

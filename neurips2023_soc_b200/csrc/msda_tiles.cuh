@@ -110,16 +110,18 @@ __device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st,
     }
 }
 
-// per-level constants of the gather
+// Per-level constants of the gather.  Row addresses are 32-bit BYTE offsets from the base of
+// the tile's (frame, head) slice; arithmetic wraps modulo 2^32, which is harmless because
+// only offsets of corners inside the map (0 <= offset < S*M*D*sizeof(T) < 2^32) are used.
 struct LevelPitch {
-    long long base;   // element offset of the virtual pixel (row -1, col -1) of the level
-    int wrow;         // elements between vertically adjacent pixels
+    uint32_t base;   // byte offset of the virtual pixel (row -1, col -1) of the level, plus the lane's slice
+    uint32_t wrow;   // bytes between vertically adjacent pixels
 };
 
-__device__ __forceinline__ LevelPitch level_pitch(const Level& L_, const int row_elems) {
+__device__ __forceinline__ LevelPitch level_pitch(const Level& L_, const uint32_t rowb, const uint32_t lane_off) {
     LevelPitch lp;
-    lp.base = ((long long)L_.start - L_.W - 1) * row_elems;
-    lp.wrow = L_.W * row_elems;
+    lp.base = (uint32_t)(L_.start - L_.W - 1) * rowb + lane_off;
+    lp.wrow = (uint32_t)L_.W * rowb;
     return lp;
 }
 

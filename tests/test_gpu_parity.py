@@ -133,7 +133,7 @@ def test_generic_and_tile_paths_agree():
     b = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
                x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_GENERIC)
     c = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
-               x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_LINEAR_TILES)
+               x.grad_output, torch.float32, torch.float32, flags=_lib.FLAG_PYRAMID_TILES)
     for i in range(4):
         assert rel_err(a[i], b[i].double().cpu().numpy()) <= 1e-5
         assert torch.equal(a[i], c[i]), "query tiling must not change a single bit"

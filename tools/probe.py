@@ -66,9 +66,9 @@ def main():
             if tag == "fp32":
                 at_med, _ = timed(lambda: msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64,
                                                                            flags=_lib.FLAG_ATOMIC_GRAD_VALUE), args.iters, flush)
-                lin_med, _ = timed(lambda: msda_ext.ms_deform_attn_forward(*a, 64, flags=_lib.FLAG_LINEAR_TILES), args.iters, flush)
+                lin_med, _ = timed(lambda: msda_ext.ms_deform_attn_forward(*a, 64, flags=_lib.FLAG_PYRAMID_TILES), args.iters, flush)
                 gen_med, _ = timed(lambda: msda_ext.ms_deform_attn_forward(*a, 64, flags=_lib.FLAG_GENERIC), max(3, args.iters // 4), flush)
-                row.update(bwd_atomic_us=at_med, fwd_linear_tiles_us=lin_med, fwd_generic_us=gen_med)
+                row.update(bwd_atomic_us=at_med, fwd_pyramid_tiles_us=lin_med, fwd_generic_us=gen_med)
                 if ref is not None:
                     rf, _ = timed(lambda: ref.ms_deform_attn_forward(*a, 64), max(3, args.iters // 2), flush)
                     rb, _ = timed(lambda: ref.ms_deform_attn_backward(*a, x.grad_output, 64), max(3, args.iters // 2), flush)
