@@ -173,9 +173,10 @@ def run_ours(args):
     queries = N * Lq
 
     def step():
-        out = msda_ext.ms_deform_attn_forward(*args_t, 64)
+        # what MSDeformAttnFunction does: the forward hands the sub-bin offsets of the inverse index on
+        out, index = msda_ext.ms_deform_attn_forward(*args_t, 64, want_index=True)
         lf = msda_ext.last_launch_count()
-        grads = msda_ext.ms_deform_attn_backward(*args_t, x.grad_output, 64)
+        grads = msda_ext.ms_deform_attn_backward(*args_t, x.grad_output, 64, index=index)
         return out, grads, lf + msda_ext.last_launch_count()
 
     def sync_all():
@@ -225,9 +226,8 @@ def run_ours(args):
     # algorithmic bytes of each kernel's own job, per launch
     alg = {
         "msda_fwd_tile_kernel": fwd_bytes,
-        "msda_bwd_sample_tile_kernel": vb * N * S * C + vb * N * Lq * C + ab * samples * 3 + ab * samples * 3,
+        "msda_bwd_sample_tile_kernel": vb * N * S * C + vb * N * Lq * C + ab * samples * 3 + ab * samples * 3 + 16 * samples,
         "msda_grad_value_walk_kernel": vb * N * Lq * C + 16 * samples + vb * N * S * C,
-        "msda_bin_fill_kernel": ab * samples * 3 + 4 * samples + 16 * samples,
         "msda_bin_sort_small_kernel": 2 * 16 * samples,
     }
     peak, peak_src = peaks()

@@ -18,6 +18,7 @@ EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",
     "msda_backward_workspace_bytes", "msda_backward", "msda_backward_ex", "msda_last_launch_count",
     "msda_profile_enable", "msda_profile_read",
+    "msda_index_bytes", "msda_forward_indexed", "msda_backward_indexed",
 )
 
 _lib = None
@@ -51,6 +52,12 @@ def load() -> ctypes.CDLL:
     lib.msda_backward.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp]
     lib.msda_backward_ex.restype = i
     lib.msda_backward_ex.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp, u]
+    lib.msda_index_bytes.restype = sz
+    lib.msda_index_bytes.argtypes = dims
+    lib.msda_forward_indexed.restype = i
+    lib.msda_forward_indexed.argtypes = [vp] * 7 + [sz] + dims + [i, i, i, vp, u]
+    lib.msda_backward_indexed.restype = i
+    lib.msda_backward_indexed.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     lib.msda_profile_enable.restype = None
     lib.msda_profile_enable.argtypes = [i]
     lib.msda_profile_read.restype = i

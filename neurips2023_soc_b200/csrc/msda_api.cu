@@ -189,8 +189,16 @@ template <typename T, typename TA, int VEC, int G, int P>
 int launch_fwd_tile(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
-    auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P>;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
+    if (p.bin_off) {   // a backward will follow: count the sub-bin populations on the way
+        auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true>;
+        prof_begin(st, "msda_fwd_tile_kernel");
+        k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+        prof_end(st);
+        MSDA_LAUNCHED("msda_fwd_tile_kernel");
+        return MSDA_OK;
+    }
+    auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false>;
     prof_begin(st, "msda_fwd_tile_kernel");
     k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     prof_end(st);
@@ -227,7 +235,7 @@ int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
             return MSDA_OK;
         }
     }
-    auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false>;
+    auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false>;   // FILL: writes the index entries
     prof_begin(st, "msda_bwd_sample_tile_kernel");
     k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     prof_end(st);
@@ -253,14 +261,13 @@ int elementwise_grid(long long items) {
     return (int)(eb < cap ? eb : cap);
 }
 
-// scan -> fill -> sort of the inverse index; `counted` says the sample kernel already took the slots
+// count + scan of the sub-bin populations into p.bin_off (when no forward handed them over)
 template <typename TA, typename CT>
-int launch_binning(const Params& p, bool counted, cudaStream_t st) {
-    const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
-    const int egrid = elementwise_grid(samples);
-    if (!counted) {
+int launch_count_scan(const Params& p, bool count, cudaStream_t st) {
+    if (count) {
+        const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
         prof_begin(st, "msda_bin_count_kernel");
-        msda_bin_count_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+        msda_bin_count_kernel<TA, CT><<<elementwise_grid(samples), kThreads, 0, st>>>(p);
         prof_end(st);
         MSDA_LAUNCHED("msda_bin_count_kernel");
     }
@@ -268,19 +275,28 @@ int launch_binning(const Params& p, bool counted, cudaStream_t st) {
     msda_bin_scan_kernel<<<p.N * p.M, 1024, 0, st>>>(p);
     prof_end(st);
     MSDA_LAUNCHED("msda_bin_scan_kernel");
+    return MSDA_OK;
+}
+
+template <typename TA, typename CT>
+int launch_fill(const Params& p, cudaStream_t st) {
+    const long long samples = (long long)p.N * p.Lq * p.M * p.LP;
     prof_begin(st, "msda_bin_fill_kernel");
-    msda_bin_fill_kernel<TA, CT><<<egrid, kThreads, 0, st>>>(p);
+    msda_bin_fill_kernel<TA, CT><<<elementwise_grid(samples), kThreads, 0, st>>>(p);
     prof_end(st);
     MSDA_LAUNCHED("msda_bin_fill_kernel");
-    {
-        const long long spans = (long long)p.N * p.M * ceil_div(p.sb_max, 32);
-        const long long sb = ceil_div(spans, kThreads / 32);
-        const long long scap = (long long)num_sms() * 8;
-        prof_begin(st, "msda_bin_sort_small_kernel");
-        msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
-        prof_end(st);
-        MSDA_LAUNCHED("msda_bin_sort_small_kernel");
-    }
+    return MSDA_OK;
+}
+
+template <typename CT>
+int launch_sort(const Params& p, cudaStream_t st) {
+    const long long spans = (long long)p.N * p.M * ceil_div(p.sb_max, 32);
+    const long long sb = ceil_div(spans, kThreads / 32);
+    const long long scap = (long long)num_sms() * 8;
+    prof_begin(st, "msda_bin_sort_small_kernel");
+    msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
+    prof_end(st);
+    MSDA_LAUNCHED("msda_bin_sort_small_kernel");
     prof_begin(st, "msda_bin_sort_big_kernel");
     msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
     prof_end(st);
@@ -371,9 +387,18 @@ int dispatch_grad_value_walk(const Params& p, const Plan& pl, int vdt, cudaStrea
     return launch_grad_value_walk<B, 8, 16>(p, st);
 }
 
+// Sub-bins per (frame, head) are only known on the device; bound them: sum_l nb_l * nch_l with
+// nb_l = (H_l+1)(W_l+1) and nch_l < 2 * (Lq*P / (6 nb_l) + 1)  =>  < L*Lq*P/3 + 2 * sum nb_l, and
+// sum nb_l <= 2S + 2L.
+int sub_bin_bound(int S, int L, int Lq, int P) { return (int)((long long)L * Lq * P / 3 + 4LL * S + 4LL * L + 1); }
+
+size_t index_bytes(int N, int S, int M, int L, int Lq, int P) {
+    return (size_t)N * M * (sub_bin_bound(S, L, Lq, P) + 1) * sizeof(uint32_t);
+}
+
 // workspace layout (bytes, every region 256-byte aligned)
 struct WsLayout {
-    size_t bin_off, counts, big, pos, entries, total;
+    size_t bin_off, cursor, counts, big, entries, total;
     int sb_max, big_cap;
 };
 
@@ -382,35 +407,55 @@ size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
     WsLayout w;
     const size_t samples = (size_t)N * Lq * M * L * P;
-    // sub-bins per (frame, head): sum_l nb_l * nch_l with nb_l = (H_l+1)(W_l+1) and
-    // nch_l < 2 * (Lq*P / (6 nb_l) + 1)  =>  < L*Lq*P/3 + 2 * sum nb_l,  sum nb_l <= 2S + 2L
-    w.sb_max = (int)((long long)L * Lq * P / 3 + 4LL * S + 4LL * L + 1);
+    w.sb_max = sub_bin_bound(S, L, Lq, P);
     w.big_cap = (int)(samples / (kBigBin + 1) + 1);
     const size_t entry = vdt == MSDA_F64 ? sizeof(Entry<double>) : sizeof(Entry<float>);
+    const size_t table = index_bytes(N, S, M, L, Lq, P);
     w.bin_off = 0;
-    // the big-list counter sits right behind the bin table so one memset clears both
-    w.counts = (size_t)N * M * (w.sb_max + 1) * sizeof(uint32_t);
+    w.cursor = align256(table);
+    w.counts = align256(w.cursor + table);
     w.big = align256(w.counts + 4 * sizeof(uint32_t));
-    w.pos = align256(w.big + 2 * (size_t)w.big_cap * sizeof(uint32_t));
-    w.entries = align256(w.pos + samples * sizeof(uint32_t));
+    w.entries = align256(w.big + 2 * (size_t)w.big_cap * sizeof(uint32_t));
     w.total = align256(w.entries + samples * entry);
     return w;
 }
 
 template <typename T, typename TA, typename CT>
-int backward_typed(Params& p, const Plan& pl, int vdt, cudaStream_t st) {
+int backward_typed(Params& p, const Plan& pl, int vdt, const void* index, size_t table_bytes, cudaStream_t st) {
     int rc;
     bool tile = pl.tile;
     if constexpr (std::is_same<T, double>::value || std::is_same<T, __half>::value) tile = false;
+    const bool atomic_arm = (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) != 0;
+    if (!atomic_arm) {
+        // sub-bin offsets: handed over by the forward, or counted and scanned here
+        if (index) {
+            prof_begin(st, "memcpy(index)");
+            MSDA_CUDA(cudaMemcpyAsync(p.bin_off, index, table_bytes, cudaMemcpyDeviceToDevice, st));
+            prof_end(st);
+            ++g_launches;
+        } else {
+            prof_begin(st, "memset(bin table)");
+            MSDA_CUDA(cudaMemsetAsync(p.bin_off, 0, table_bytes, st));
+            prof_end(st);
+            ++g_launches;
+            if ((rc = launch_count_scan<TA, CT>(p, true, st))) return rc;
+        }
+        prof_begin(st, "memcpy(cursor)");
+        MSDA_CUDA(cudaMemcpyAsync(p.cursor, p.bin_off, table_bytes, cudaMemcpyDeviceToDevice, st));
+        MSDA_CUDA(cudaMemsetAsync(p.counts, 0, 4 * sizeof(uint32_t), st));
+        prof_end(st);
+        g_launches += 2;
+    }
     if (tile) {
         if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
             if ((rc = dispatch_bwd_sample_tile<TA>(p, pl, vdt, st))) return rc;
         }
     } else {
         if ((rc = launch_bwd_sample_generic<T, TA, CT>(p, st))) return rc;
+        if (!atomic_arm && (rc = launch_fill<TA, CT>(p, st))) return rc;
     }
-    if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) return MSDA_OK;
-    if ((rc = launch_binning<TA, CT>(p, /*counted=*/tile, st))) return rc;
+    if (atomic_arm) return MSDA_OK;
+    if ((rc = launch_sort<CT>(p, st))) return rc;
     if (tile) return dispatch_grad_value_walk(p, pl, vdt, st);
     return launch_grad_value_generic<T, CT>(p, st);
 }
@@ -456,10 +501,16 @@ int msda_profile_read(char* names, size_t names_cap, float* ms, int cap) {
     return n;
 }
 
-int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                    const void* sampling_loc, const void* attn_weight, void* output, int N, int S, int M,
-                    int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
-                    void* cuda_stream, unsigned flags) {
+size_t msda_index_bytes(int N, int S, int M, int D, int L, int Lq, int P) {
+    (void)D;
+    if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || Lq <= 0 || P <= 0) return 0;
+    return index_bytes(N, S, M, L, Lq, P);
+}
+
+int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const void* sampling_loc, const void* attn_weight, void* output, void* index,
+                         size_t index_size, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                         int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
     g_launches = 0;
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
@@ -474,6 +525,17 @@ int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int6
     p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = L * P;
     p.id_shift = id_shift_for(p.LP);
     p.flags = flags;
+    p.sb_max = sub_bin_bound(S, L, Lq, P);
+    if (index) {
+        const size_t need = index_bytes(N, S, M, L, Lq, P);
+        if (index_size < need || !aligned16(index))
+            return fail(MSDA_ERR_WORKSPACE, "index buffer of %zu bytes (16-byte aligned) required, got %zu", need, index_size);
+        p.bin_off = static_cast<uint32_t*>(index);
+        prof_begin(st, "memset(index)");
+        MSDA_CUDA(cudaMemsetAsync(index, 0, need, st));
+        prof_end(st);
+        ++g_launches;
+    }
 
     Plan pl = make_plan(D, P, value_dtype, flags);
     if (pl.tile && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight)))
@@ -482,22 +544,42 @@ int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int6
     if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 32)) pl.tile = false;  // 32-bit byte offsets
 
     const bool aux32 = aux_dtype == MSDA_F32;
+    const bool tile = pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16);
     switch (value_dtype) {
         case MSDA_F32:
-            return pl.tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st)
-                           : launch_fwd_generic<float, float, float>(p, st);
+            rc = tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st) : launch_fwd_generic<float, float, float>(p, st);
+            break;
         case MSDA_BF16:
             if (aux32)
-                return pl.tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st)
-                               : launch_fwd_generic<__nv_bfloat16, float, float>(p, st);
-            return pl.tile ? dispatch_fwd_tile<__nv_bfloat16>(p, pl, value_dtype, st)
-                           : launch_fwd_generic<__nv_bfloat16, __nv_bfloat16, float>(p, st);
+                rc = tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st)
+                          : launch_fwd_generic<__nv_bfloat16, float, float>(p, st);
+            else
+                rc = tile ? dispatch_fwd_tile<__nv_bfloat16>(p, pl, value_dtype, st)
+                          : launch_fwd_generic<__nv_bfloat16, __nv_bfloat16, float>(p, st);
+            break;
         case MSDA_F16:
-            return aux32 ? launch_fwd_generic<__half, float, float>(p, st)
-                         : launch_fwd_generic<__half, __half, float>(p, st);
+            rc = aux32 ? launch_fwd_generic<__half, float, float>(p, st) : launch_fwd_generic<__half, __half, float>(p, st);
+            break;
         default:
-            return launch_fwd_generic<double, double, double>(p, st);
+            rc = launch_fwd_generic<double, double, double>(p, st);
     }
+    if (rc || !index) return rc;
+    // the tile kernel counted on the way; the generic kernels leave that to a separate pass
+    const bool count_now = !tile;
+    switch (aux_dtype) {
+        case MSDA_F32: return launch_count_scan<float, float>(p, count_now, st);
+        case MSDA_BF16: return launch_count_scan<__nv_bfloat16, float>(p, count_now, st);
+        case MSDA_F16: return launch_count_scan<__half, float>(p, count_now, st);
+        default: return launch_count_scan<double, double>(p, count_now, st);
+    }
+}
+
+int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                    const void* sampling_loc, const void* attn_weight, void* output, int N, int S, int M,
+                    int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
+                    void* cuda_stream, unsigned flags) {
+    return msda_forward_indexed(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, nullptr,
+                                0, N, S, M, D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags);
 }
 
 int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
@@ -514,11 +596,12 @@ size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, 
     return ws_layout(N, S, M, L, Lq, P, value_dtype).total;
 }
 
-int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                     const void* sampling_loc, const void* attn_weight, const void* grad_output,
-                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
-                     size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
-                     int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
+int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                          size_t workspace_bytes, const void* index, size_t index_size, int N, int S, int M, int D,
+                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
+                          unsigned flags) {
     g_launches = 0;
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
@@ -539,6 +622,9 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
                     workspace ? workspace_bytes : (size_t)0);
     if (need_ws && !aligned16(workspace))
         return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    const size_t table_bytes = index_bytes(N, S, M, L, Lq, P);
+    if (index && index_size < table_bytes)
+        return fail(MSDA_ERR_WORKSPACE, "index buffer of %zu bytes required, got %zu", table_bytes, index_size);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 
     Params p;
@@ -553,14 +639,10 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
     if (need_ws) {
         char* base = static_cast<char*>(workspace);
         p.bin_off = reinterpret_cast<uint32_t*>(base + w.bin_off);
+        p.cursor = reinterpret_cast<uint32_t*>(base + w.cursor);
         p.counts = reinterpret_cast<uint32_t*>(base + w.counts);
         p.big_bins = reinterpret_cast<uint32_t*>(base + w.big);
-        p.pos = reinterpret_cast<uint32_t*>(base + w.pos);
         p.entries = base + w.entries;
-        prof_begin(st, "memset(bin table)");
-        MSDA_CUDA(cudaMemsetAsync(base + w.bin_off, 0, w.counts + 4 * sizeof(uint32_t), st));
-        prof_end(st);
-        ++g_launches;
     } else {
         MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)N * S * M * D * dtype_size(value_dtype), st));
         ++g_launches;
@@ -573,15 +655,25 @@ int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {
-        case MSDA_F32: return backward_typed<float, float, float>(p, pl, value_dtype, st);
+        case MSDA_F32: return backward_typed<float, float, float>(p, pl, value_dtype, index, table_bytes, st);
         case MSDA_BF16:
-            return aux32 ? backward_typed<__nv_bfloat16, float, float>(p, pl, value_dtype, st)
-                         : backward_typed<__nv_bfloat16, __nv_bfloat16, float>(p, pl, value_dtype, st);
+            return aux32 ? backward_typed<__nv_bfloat16, float, float>(p, pl, value_dtype, index, table_bytes, st)
+                         : backward_typed<__nv_bfloat16, __nv_bfloat16, float>(p, pl, value_dtype, index, table_bytes, st);
         case MSDA_F16:
-            return aux32 ? backward_typed<__half, float, float>(p, pl, value_dtype, st)
-                         : backward_typed<__half, __half, float>(p, pl, value_dtype, st);
-        default: return backward_typed<double, double, double>(p, pl, value_dtype, st);
+            return aux32 ? backward_typed<__half, float, float>(p, pl, value_dtype, index, table_bytes, st)
+                         : backward_typed<__half, __half, float>(p, pl, value_dtype, index, table_bytes, st);
+        default: return backward_typed<double, double, double>(p, pl, value_dtype, index, table_bytes, st);
     }
+}
+
+int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                     const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                     size_t workspace_bytes, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                     int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
+    return msda_backward_indexed(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                 grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes, nullptr,
+                                 0, N, S, M, D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags);
 }
 
 int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

@@ -41,7 +41,6 @@
 
 namespace msda {
 
-constexpr uint32_t kRejected = 0xffffffffu;
 constexpr int kBigBin = 32;  // bins with more entries are sorted by msda_bin_sort_big_kernel
 
 template <typename CT> struct Entry;
@@ -85,10 +84,11 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
 #define MSDA_BWD_MIN_BLOCKS 3
 #endif
 
-// COUNT: the staging threads also take each accepted sample's slot in the inverse index of
-// part B (integer atomics, overlapped with the gather).  ATOMIC: bench-only A/B arm that
-// scatters grad_value with 128-bit fp32 reductions like the reference does with scalar ones.
-template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool ATOMIC>
+// FILL: the staging threads also write each accepted sample's entry into the inverse index of
+// part B (one integer atomic + one 16-byte store, overlapped with the gather).  ATOMIC:
+// bench-only A/B arm that scatters grad_value with 128-bit fp32 reductions like the reference
+// does with scalar ones.
+template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
     stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, COUNT>(st, p, lv, tl, cur, desc[0]);
+    stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, tl, cur, desc[0]);
     __syncthreads();
 
     int buf = 0;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
             }
         }
 
-        if (has_next) stage_build<G, P, COUNT>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        if (has_next) stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
         __syncthreads();
         if (!has_next) break;
         cur = nxt;
@@ -352,17 +352,14 @@ __global__ void __launch_bounds__(kThreads) msda_bin_count_kernel(const Params p
         const Level L_ = lv[r.l];
         const XY<CT> xy = load_xy(loc + 2 * si);
         const Sample<CT> s = locate(xy.x, xy.y, L_.H, L_.W);
-        uint32_t slot = kRejected;
         if (s.ok) {
             const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
-            slot = atomicAdd(p.bin_off + (size_t)(r.n * p.M + r.m) * (p.sb_max + 1) + bin, 1u);
+            atomicAdd(p.bin_off + (size_t)(r.n * p.M + r.m) * (p.sb_max + 1) + bin, 1u);
         }
-        p.pos[si] = slot;
     }
 }
 
-// One CTA per (frame, head): in-place exclusive scan of the sub-bin counts.  Sub-bins with
-// more than kBigBin entries are appended to the big list (sorted by one CTA each).
+// One CTA per (frame, head): in-place exclusive scan of the sub-bin counts.
 __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
@@ -375,15 +372,7 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
     const int beg = min(SB, (int)threadIdx.x * ipt), end = min(SB, beg + ipt);
     uint32_t sum = 0;
     for (int i = beg; i < end; ++i) {
-        const uint32_t c = data[i];
-        sum += c;
-        if (c > (uint32_t)kBigBin) {
-            const uint32_t k = atomicAdd(p.counts + 0, 1u);
-            if (k < (uint32_t)p.big_cap) {
-                p.big_bins[2 * k] = (uint32_t)nm;
-                p.big_bins[2 * k + 1] = (uint32_t)i;
-            }
-        }
+        sum += data[i];
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = sum;
@@ -424,20 +413,19 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
     const size_t per_nm = (size_t)p.Lq * p.LP;
     const size_t total = (size_t)p.N * p.Lq * p.M * p.LP;
     for (size_t si = (size_t)blockIdx.x * blockDim.x + threadIdx.x; si < total; si += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t slot = p.pos[si];
-        if (slot == kRejected) continue;
         const SampleRef r = sample_ref(p, si);
         const Level L_ = lv[r.l];
         const XY<CT> xy = load_xy(loc + 2 * si);
         const Sample<CT> s = locate(xy.x, xy.y, L_.H, L_.W);
+        if (!s.ok) continue;
         const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
         const size_t nm = (size_t)r.n * p.M + r.m;
-        const uint32_t base = p.bin_off[nm * (p.sb_max + 1) + bin];
+        const uint32_t slot = atomicAdd(p.cursor + nm * (p.sb_max + 1) + bin, 1u);
         Entry<CT> e;
         e.id = ((uint32_t)r.q << p.id_shift) | (uint32_t)r.sg;
         e.lh = s.lh; e.lw = s.lw;
         e.a = (CT)Elem<TA>::to_f(attn[si]);
-        entries[nm * per_nm + base + slot] = e;
+        entries[nm * per_nm + slot] = e;
     }
 }
 
@@ -448,8 +436,20 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
 
 template <typename CT, int WIDTH>
 __device__ __forceinline__ void sort_in_lanes(Entry<CT>* base, const uint32_t cnt, const int sub, const uint32_t mask) {
-    // `sub` = lane index inside a WIDTH-lane segment; one entry per lane.
-    uint32_t key = sub < (int)cnt ? base[sub].id : 0xffffffffu;
+    // `sub` = lane index inside a WIDTH-lane segment; one entry per lane, read once.
+    constexpr int NW = sizeof(Entry<CT>) / 4;
+    uint32_t w[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) w[i] = 0xffffffffu;
+    if (sub < (int)cnt) {
+        const uint4* src4 = reinterpret_cast<const uint4*>(base + sub);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+            const uint4 t = src4[i];
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+    }
+    uint32_t key = w[0];          // Entry::id is the first word; empty lanes hold +inf
     int src = sub;
 #pragma unroll
     for (int k = 2; k <= WIDTH; k <<= 1) {
@@ -463,11 +463,15 @@ __device__ __forceinline__ void sort_in_lanes(Entry<CT>* base, const uint32_t cn
             if (j == 1 || (j == k - 1 && k == 2)) break;
         }
     }
-    // lane `sub` now knows which original slot belongs at position `sub`
-    Entry<CT> e;
-    if (sub < (int)cnt) e = base[src];
-    __syncwarp(mask);
-    if (sub < (int)cnt) base[sub] = e;
+    // position `sub` receives the entry that lane `src` loaded
+    uint32_t o[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) o[i] = __shfl_sync(mask, w[i], src, WIDTH);
+    if (sub < (int)cnt) {
+        uint4* dst4 = reinterpret_cast<uint4*>(base + sub);
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) dst4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
 }
 
 // Sub-bins of up to 32 entries, sorted in place.  A warp takes 32 consecutive sub-bins: their
@@ -497,6 +501,13 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_small_kernel(const Par
             cnt = off[b + 1] - beg;
         }
         Entry<CT>* ent = entries + nm * per_nm;
+        if (cnt > (uint32_t)kBigBin) {              // left to msda_bin_sort_big_kernel
+            const uint32_t k = atomicAdd(p.counts, 1u);
+            if (k < (uint32_t)p.big_cap) {
+                p.big_bins[2 * k] = (uint32_t)nm;
+                p.big_bins[2 * k + 1] = (uint32_t)b;
+            }
+        }
 #pragma unroll 2
         for (int j = 0; j < 8; ++j) {
             const uint32_t sbeg = __shfl_sync(0xffffffffu, beg, seg * 8 + j);

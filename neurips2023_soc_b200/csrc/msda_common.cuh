@@ -41,8 +41,8 @@ struct Params {
     void* grad_loc;
     void* grad_attn;
     // backward workspace (see msda_backward.cuh)
-    uint32_t* bin_off;       // [N*M][sb_max + 1]  counts, then exclusive offsets
-    uint32_t* pos;           // [N*Lq*M*L*P]       slot of each sample inside its bin
+    uint32_t* bin_off;       // [N*M][sb_max + 1]  sub-bin counts, then their exclusive scan
+    uint32_t* cursor;        // [N*M][sb_max + 1]  copy of the offsets that the fill advances
     void* entries;           // [N*M][Lq*L*P]      per-bin contribution lists
     uint32_t* counts;        // [0] entries in big_bins (right behind bin_off so one memset clears both)
     uint32_t* big_bins;      // (nm, sub-bin) pairs of sub-bins with > 32 entries

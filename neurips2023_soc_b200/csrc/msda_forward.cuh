@@ -32,8 +32,10 @@ namespace msda {
 
 // T value dtype, TA location/weight dtype, VEC channels per lane, G = D / VEC lanes per row,
 // P points per level (compile time so that the per-level constants hoist out of the loop).
-template <typename T, typename TA, int VEC, int G, int P>
+// COUNT: also count the accepted samples per sub-bin for a backward that will follow.
+template <typename T, typename TA, int VEC, int G, int P, bool COUNT>
 __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_kernel(const Params p, const int rounds) {
+    constexpr int MODE = COUNT ? kIndexCount : kIndexNone;
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
     constexpr int LPC = (P >= kSC) ? 1 : kSC / P;   // levels per 16-sample chunk
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
     stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, false>(st, p, lv, tl, cur, desc[0]);
+    stage_build<G, P, MODE>(st, p, lv, tl, cur, desc[0]);
     __syncthreads();
 
     int buf = 0;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
                 store_row<T, VEC>(out + (((size_t)tl.n * p.Lq + q_mine) * p.M + tl.m) * p.D + gl * VEC, acc);
         }
 
-        if (has_next) stage_build<G, P, false>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        if (has_next) stage_build<G, P, MODE>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
         __syncthreads();
         if (!has_next) break;
         cur = nxt;

@@ -74,9 +74,18 @@ __device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const 
     }
 }
 
-// Turn the staged locations into descriptors.  With COUNT the accepted samples also take
-// their slot in the inverse index used by the grad_value gather (msda_backward.cuh, part B).
-template <int G, int P, bool COUNT>
+// What the staging threads do for the inverse index of the grad_value gather
+// (msda_backward.cuh, part B) while they build descriptors:
+//   kIndexNone   nothing (plain forward)
+//   kIndexCount  count the accepted samples of every sub-bin (forward that will be followed by a
+//                backward: the scan of these counts is handed to it)
+//   kIndexFill   take a slot from the sub-bin's cursor (initialised to its exclusive offset)
+//                and write the sample's 16-byte entry there (backward)
+// Only integer atomics are involved; they decide where an entry sits before sorting, never a
+// floating-point result.
+constexpr int kIndexNone = 0, kIndexCount = 1, kIndexFill = 2;
+
+template <int G, int P, int MODE>
 __device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
                                             const Tile& tl, const Work& w, uint4* __restrict__ desc) {
     constexpr int DPT = TileShape<G>::DPT;
@@ -90,7 +99,6 @@ __device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st,
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
         if (st.q[k] >= 0) {
             const Sample<float> s = locate(st.x[k], st.y[k], L_.H, L_.W);
-            uint32_t slot = 0xffffffffu;
             if (s.ok) {
                 const unsigned h0 = s.h_lo >= 0, w0 = s.w_lo >= 0;
                 const unsigned h1 = s.h_lo + 1 <= L_.H - 1, w1 = s.w_lo + 1 <= L_.W - 1;
@@ -99,12 +107,20 @@ __device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st,
                 d.y = __float_as_uint(s.lh);
                 d.z = __float_as_uint(s.lw);
                 d.w = __float_as_uint(st.a[k]);
-                if constexpr (COUNT)
-                    slot = atomicAdd(p.bin_off + (size_t)(tl.n * p.M + tl.m) * (p.sb_max + 1) +
-                                         sub_bin(L_, s.h_lo, s.w_lo, st.q[k]), 1u);
+                if constexpr (MODE != kIndexNone) {
+                    const size_t nm = (size_t)tl.n * p.M + tl.m;
+                    const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]);
+                    if constexpr (MODE == kIndexCount) {
+                        atomicAdd(p.bin_off + b, 1u);
+                    } else {
+                        const uint32_t slot = atomicAdd(p.cursor + b, 1u);
+                        uint4 e;
+                        e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;
+                        e.y = d.y; e.z = d.z; e.w = d.w;
+                        static_cast<uint4*>(p.entries)[nm * ((size_t)p.Lq * p.LP) + slot] = e;
+                    }
+                }
             }
-            if constexpr (COUNT)
-                p.pos[(((size_t)tl.n * p.Lq + st.q[k]) * p.M + tl.m) * p.LP + sg] = slot;
         }
         desc[j * kDescStride + st_s] = d;
     }

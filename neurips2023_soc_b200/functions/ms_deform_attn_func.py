@@ -39,8 +39,12 @@ class MSDeformAttnFunction(Function):
         loc = sampling_locations.to(aux).contiguous()
         attn = attention_weights.to(aux).contiguous()
         value = value.contiguous()
-        output = msda_ext.ms_deform_attn_forward(
-            value, value_spatial_shapes, value_level_start_index, loc, attn, ctx.im2col_step)
+        # when a backward will follow, the forward also leaves the sub-bin offsets of the
+        # grad_value gather's inverse index (a pure function of the saved inputs)
+        want_index = any(ctx.needs_input_grad[i] for i in (0, 3, 4))
+        res = msda_ext.ms_deform_attn_forward(
+            value, value_spatial_shapes, value_level_start_index, loc, attn, ctx.im2col_step, want_index=want_index)
+        output, ctx.index = res if want_index else (res, None)
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, loc, attn)
         return output
 
@@ -49,5 +53,7 @@ class MSDeformAttnFunction(Function):
     def backward(ctx, grad_output):
         value, shapes, lsi, loc, attn = ctx.saved_tensors
         grad_value, grad_loc, grad_attn = msda_ext.ms_deform_attn_backward(
-            value, shapes, lsi, loc, attn, grad_output.to(value.dtype).contiguous(), ctx.im2col_step)
+            value, shapes, lsi, loc, attn, grad_output.to(value.dtype).contiguous(), ctx.im2col_step,
+            index=ctx.index)
+        ctx.index = None
         return grad_value, None, None, grad_loc.to(ctx.aux_in[0]), grad_attn.to(ctx.aux_in[1]), None

@@ -69,7 +69,9 @@ def _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                           im2col_step: int, flags: int | None = None) -> torch.Tensor:
+                           im2col_step: int, flags: int | None = None, want_index: bool = False):
+    """``want_index=True`` (not part of the reference signature) also returns the index the matching
+    backward can reuse: ``(output, index)`` -- see msda_forward_indexed in include/msda_b200.h."""
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
     dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
@@ -78,15 +80,20 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     with torch.cuda.device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.msda_forward_ex(
+        index, index_ptr, index_bytes = None, None, 0
+        if want_index:
+            index_bytes = int(lib.msda_index_bytes(*dims))
+            index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
+            index_ptr = index.data_ptr()
+        _lib.check(lib.msda_forward_indexed(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(), index_ptr, index_bytes,
             *dims, vdt, adt, int(im2col_step), stream, DEFAULT_FLAGS if flags is None else flags))
-    return out
+    return (out, index) if want_index else out
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step: int, flags: int | None = None) -> List[torch.Tensor]:
+                            im2col_step: int, flags: int | None = None, index=None) -> List[torch.Tensor]:
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
     dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
@@ -102,11 +109,12 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         ws_bytes = 0 if flags & _lib.FLAG_ATOMIC_GRAD_VALUE else int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.msda_backward_ex(
+        _lib.check(lib.msda_backward_indexed(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
-            ws.data_ptr(), ws_bytes, *dims, vdt, adt, int(im2col_step), stream, flags))
+            ws.data_ptr(), ws_bytes, None if index is None else index.data_ptr(),
+            0 if index is None else index.numel(), *dims, vdt, adt, int(im2col_step), stream, flags))
         # `ws` may be released to the caching allocator here: reuse is ordered on this stream
     return [grad_value, grad_loc, grad_attn]
 

@@ -26,11 +26,12 @@ REF = Path("/root/reference")
 pytestmark = pytest.mark.skipif(not (REF / "models" / "ops").exists(), reason="reference sources not present")
 
 
-def _oracle_forward(value, shapes, lsi, loc, attn, im2col_step, flags=None):
-    return torch.from_numpy(O.forward_c(value, shapes, lsi, loc, attn, dtype=np.float32))
+def _oracle_forward(value, shapes, lsi, loc, attn, im2col_step, flags=None, want_index=False):
+    out = torch.from_numpy(O.forward_c(value, shapes, lsi, loc, attn, dtype=np.float32))
+    return (out, None) if want_index else out
 
 
-def _oracle_backward(value, shapes, lsi, loc, attn, grad_out, im2col_step, flags=None):
+def _oracle_backward(value, shapes, lsi, loc, attn, grad_out, im2col_step, flags=None, index=None):
     return [torch.from_numpy(a) for a in O.backward_c(value, shapes, lsi, loc, attn, grad_out, dtype=np.float32)]
 
 

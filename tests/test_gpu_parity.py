@@ -45,6 +45,11 @@ def run_op(value, shapes, lsi, loc, attn, grad_out, vdt, adt, flags=0):
     go = grad_out.to(DEV, vdt).contiguous()
     out = msda_ext.ms_deform_attn_forward(v, sh, ls, lo, at, 64, flags=flags)
     gv, gl, ga = msda_ext.ms_deform_attn_backward(v, sh, ls, lo, at, go, 64, flags=flags)
+    if not flags & _lib.FLAG_ATOMIC_GRAD_VALUE:
+        # the index handed over by the forward must reproduce the self-counted backward bit for bit
+        out2, index = msda_ext.ms_deform_attn_forward(v, sh, ls, lo, at, 64, flags=flags, want_index=True)
+        gv2, gl2, ga2 = msda_ext.ms_deform_attn_backward(v, sh, ls, lo, at, go, 64, flags=flags, index=index)
+        assert torch.equal(out, out2) and torch.equal(gv, gv2) and torch.equal(gl, gl2) and torch.equal(ga, ga2)
     torch.cuda.synchronize()
     return out, gv, gl, ga, (v, lo, at, go)
 

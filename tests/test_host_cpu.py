@@ -48,8 +48,10 @@ def test_workspace_size(lib):
     big = lib.msda_backward_workspace_bytes(16, 5100, 8, 32, 4, 5100, 4, 0, 0)
     assert 0 < small < big
     samples = 16 * 5100 * 8 * 16
-    assert big >= samples * (16 + 4)                      # entries + slot per sample
-    assert big < samples * (16 + 4) + (64 << 20)          # plus the bin tables, nothing more
+    assert big >= samples * 16                            # one 16-byte entry per sample
+    assert big < samples * 16 + (64 << 20)                # plus the bin tables, nothing more
+    idx = lib.msda_index_bytes(16, 5100, 8, 32, 4, 5100, 4)
+    assert 0 < idx < (32 << 20)
     assert lib.msda_backward_workspace_bytes(0, 1, 1, 1, 1, 1, 1, 0, 0) == 0
 
 

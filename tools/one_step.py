@@ -21,7 +21,9 @@ vdt, adt = {"fp32": (torch.float32, torch.float32), "bf16mix": (torch.bfloat16, 
 x = make_inputs(N=a.N, dist=a.dist, seed=0).to("cuda:0", vdt, adt)
 args = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
 for _ in range(a.steps):
-    msda_ext.ms_deform_attn_forward(*args, 64)
-    if not a.fwd_only:
-        msda_ext.ms_deform_attn_backward(*args, x.grad_output, 64)
+    if a.fwd_only:
+        msda_ext.ms_deform_attn_forward(*args, 64)
+    else:
+        _, index = msda_ext.ms_deform_attn_forward(*args, 64, want_index=True)
+        msda_ext.ms_deform_attn_backward(*args, x.grad_output, 64, index=index)
 torch.cuda.synchronize()
