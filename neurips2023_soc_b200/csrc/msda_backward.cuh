@@ -615,21 +615,33 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
     constexpr int GW = 32 / G;                   // groups per warp
     constexpr int BR = (512 / D) < 2 ? 2 : (512 / D);   // bin rows per tile
     constexpr int TH = BR - 1, TW = kGTileW;
-    constexpr int STEP = 4;                      // grad_output rows in flight per lane
+    constexpr int STEP = VEC <= 4 ? 8 : 4;       // grad_output rows in flight per lane
+    constexpr int NWARP = kGThreads / 32;
+    // dense levels (many entries per bin) use small tiles -- one bin row per warp, 4 pixels wide -- so
+    // that their long lists spread over many CTAs; the others use the full TH x TW tile
+    constexpr int TH_D = NWARP - 1 < TH ? NWARP - 1 : TH, TW_D = 4;
 
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
-    __shared__ int tstart[kMaxLevels + 1];
+    __shared__ int tstart[kMaxLevels + 1];   // first tile of each level in the launch-wide order
+    __shared__ int s_tile;
     __shared__ __align__(16) float sT[TH * TW * D];
     __shared__ __align__(16) float sB[TH * TW * D];
     load_levels(p, lv, &s_sb, &s_sq);
+    auto is_dense = [&](const int l) { return GW > 1 && lv[l].nch_log2 >= 3; };
+    auto tiles_of = [&](const int l) {
+        const int th = is_dense(l) ? TH_D : TH, tw = is_dense(l) ? TW_D : TW;
+        return ((lv[l].H + th - 1) / th) * ((lv[l].W + tw - 1) / tw);
+    };
     if (threadIdx.x == 0) {
+        // launch-wide order: coarsest level first (its tiles carry the longest lists), all frames and
+        // heads of a level before the next level
         int t = 0;
-        for (int l = 0; l < p.L; ++l) {
+        for (int l = p.L - 1; l >= 0; --l) {
             tstart[l] = t;
-            t += ((lv[l].H + TH - 1) / TH) * ((lv[l].W + TW - 1) / TW);
+            t += p.N * p.M * tiles_of(l);
         }
-        tstart[p.L] = t;
+        tstart[p.L] = t;     // total
     }
     __syncthreads();
 
@@ -640,25 +652,29 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / G, gl = tid % G, gw = lane / G;    // gw: group index inside the warp
     const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
-    const int per_nm_tiles = tstart[p.L];
-    const int total_tiles = p.N * p.M * per_nm_tiles;
+    const int total_tiles = tstart[p.L];
     const size_t per_nm = (size_t)p.Lq * p.LP;
     const size_t qstride = (size_t)p.M * p.D;
 
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n = t / (per_nm_tiles * p.M);
-        const int r = t - n * per_nm_tiles * p.M;
-        const int lt = per_nm_tiles - 1 - r / p.M;        // coarse (dense) levels first
-        const int m = r % p.M;
-        int l = 0;
-        while (l + 1 < p.L && lt >= tstart[l + 1]) ++l;
+    while (true) {
+        // dynamic tile scheduler: heavy tiles first, no CTA is handed two of them while others idle
+        if (tid == 0) s_tile = (int)atomicAdd(p.counts + 1, 1u);
+        __syncthreads();
+        const int t = s_tile;
+        if (t >= total_tiles) break;
+        int l = p.L - 1;
+        while (l > 0 && t >= tstart[l - 1]) --l;
         const Level L_ = lv[l];
-        const int tw = (L_.W + TW - 1) / TW;
-        const int k = lt - tstart[l];
-        const int y0 = (k / tw) * TH, x0 = (k % tw) * TW;
-        const int nb = min(x0 + TW, L_.W) - x0 + 1;       // bins walked per row: x0 .. min(x0+TW, W)
-        // dense: a bin holds enough entries to keep every group of a warp busy
-        const bool dense = GW > 1 && (1 << L_.nch_log2) * kSubBinTarget >= 4 * G * GW;
+        const bool dense = is_dense(l);                    // the groups of a warp share each bin
+        const int th_l = dense ? TH_D : TH, tw_l = dense ? TW_D : TW;
+        const int tiles_x = (L_.W + tw_l - 1) / tw_l;
+        const int tiles_l = tiles_x * ((L_.H + th_l - 1) / th_l);
+        const int rem = t - tstart[l];
+        const int n = rem / (tiles_l * p.M);
+        const int r2 = rem - n * tiles_l * p.M;
+        const int k = r2 / p.M, m = r2 - k * p.M;
+        const int y0 = (k / tiles_x) * th_l, x0 = (k % tiles_x) * tw_l;
+        const int nb = min(x0 + tw_l, L_.W) - x0 + 1;      // bins walked per row: x0 .. min(x0+tw, W)
 
         const size_t nm = (size_t)n * p.M + m;
         const uint32_t* off = p.bin_off + nm * (p.sb_max + 1);
@@ -666,12 +682,12 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
         const T* gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
 
         const int row_first = dense ? warp : grp;
-        const int row_step = dense ? kGThreads / 32 : NGRP;
-        for (int row = row_first; row < BR; row += row_step) {
+        const int row_step = dense ? NWARP : NGRP;
+        for (int row = row_first; row <= th_l; row += row_step) {
             const int by = y0 + row;
             if (by > L_.H) break;
             const bool emit_t = row >= 1;                              // pixel row by-1 is in the tile
-            const bool emit_b = row <= TH - 1 && by <= L_.H - 1;       // pixel row by is in the tile
+            const bool emit_b = row <= th_l - 1 && by <= L_.H - 1;     // pixel row by is in the tile
             float* const tdst = sT + (row - 1) * TW * D + gl * VEC;
             float* const bdst = sB + row * TW * D + gl * VEC;
 
@@ -773,10 +789,10 @@ __global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const P
             }
         }
         __syncthreads();
-        for (int i = tid; i < TH * TW * G; i += kGThreads) {
+        for (int i = tid; i < th_l * TW * G; i += kGThreads) {
             const int c = i % G, px = (i / G) % TW, py = i / (G * TW);
             const int y = y0 + py, x = x0 + px;
-            if (y < L_.H && x < L_.W) {
+            if (px < tw_l && y < L_.H && x < L_.W) {
                 float v[VEC];
                 const float* a = sT + (py * TW + px) * D + c * VEC;
                 const float* b = sB + (py * TW + px) * D + c * VEC;
