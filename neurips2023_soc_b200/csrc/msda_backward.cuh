@@ -203,31 +203,36 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
             }
             reduce_scatter<G, NV>(part, gl);
 
-            // lane gl now holds the complete corner sums with indices [gl*CPL, gl*CPL + CPL)
+            // Lane gl now holds the complete corner sums with indices [gl*CPL, gl*CPL + CPL): whole
+            // samples (CPL >= 4), the top or bottom corner pair of one (CPL == 2), or one corner (CPL == 1).
+            //   grad_attn = hh hw d0 + hh lw d1 + lh hw d2 + lh lw d3
+            //   dX = hh (d1 - d0) + lh (d3 - d2)        dY = hw (d2 - d0) + lw (d3 - d1)      (cuh:116-158)
 #pragma unroll
             for (int i = 0; i < SPL; ++i) {
                 const int s = (gl * CPL) / 4 + i;            // sample inside this level step
-                const int k0 = (gl * CPL) & 3;               // first corner this lane holds (0 unless LPS > 1)
                 const uint4 d = drow[sbase + s];
                 const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
                 const float hh = 1.f - lh, hw = 1.f - lw;
-                // contribution of corner k to (grad_attn, dX, dY): coefficients (cuh:116-158)
-                const float ca[4] = {hh * hw, hh * lw, lh * hw, lh * lw};
-                const float cx[4] = {-hh, hh, -lh, lh};
-                const float cy[4] = {-hw, -lw, hw, lw};
-                float ga = 0.f, gx = 0.f, gy = 0.f;
-#pragma unroll
-                for (int j = 0; j < (CPL < 4 ? CPL : 4); ++j) {
-                    const float dv = part[4 * i + j];
-                    float fa = ca[j], fx = cx[j], fy = cy[j];
-                    if constexpr (LPS > 1) {                 // k0 + j picks the coefficient at run time
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (k0 + j == k) { fa = ca[k]; fx = cx[k]; fy = cy[k]; }
-                    }
-                    ga = fmaf(fa, dv, ga);
-                    gx = fmaf(fx, dv, gx);
-                    gy = fmaf(fy, dv, gy);
+                float ga, gx, gy;
+                if constexpr (CPL >= 4) {
+                    const float d0 = part[4 * i], d1 = part[4 * i + 1], d2 = part[4 * i + 2], d3 = part[4 * i + 3];
+                    ga = hh * (hw * d0 + lw * d1) + lh * (hw * d2 + lw * d3);
+                    gx = hh * (d1 - d0) + lh * (d3 - d2);
+                    gy = hw * (d2 - d0) + lw * (d3 - d1);
+                } else if constexpr (CPL == 2) {
+                    const bool bottom = (gl & 1) != 0;       // odd lanes hold (d2, d3), even lanes (d0, d1)
+                    const float rowf = bottom ? lh : hh;
+                    const float t = hw * part[0] + lw * part[1];
+                    ga = rowf * t;
+                    gx = rowf * (part[1] - part[0]);
+                    gy = bottom ? t : -t;
+                } else {
+                    const bool bottom = (gl & 2) != 0, right = (gl & 1) != 0;   // corner k = gl & 3
+                    const float rowf = bottom ? lh : hh, colf = right ? lw : hw;
+                    const float dv = part[0];
+                    ga = rowf * colf * dv;
+                    gx = rowf * (right ? dv : -dv);
+                    gy = colf * (bottom ? dv : -dv);
                 }
                 if constexpr (LPS > 1) {
 #pragma unroll
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                     }
                 }
                 const int sgo = cur.c0 + sbase + s;
-                if (q_mine >= 0 && k0 == 0 && sgo < p.LP) {
+                if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
                     const size_t si = qm_mine * p.LP + sgo;
                     gattn[si] = Elem<TA>::from_f(ga);
                     gloc[2 * si] = Elem<TA>::from_f((float)L_.W * a * gx);
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) msda_bin_sort_small_kernel(const Par
                 p.big_bins[2 * k + 1] = (uint32_t)b;
             }
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < 8; ++j) {
             const uint32_t sbeg = __shfl_sync(0xffffffffu, beg, seg * 8 + j);
             const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, seg * 8 + j);
