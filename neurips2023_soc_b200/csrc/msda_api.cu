@@ -429,10 +429,8 @@ int backward_typed(Params& p, const Plan& pl, int vdt, const void* index, size_t
     if (!atomic_arm) {
         // sub-bin offsets: handed over by the forward, or counted and scanned here
         if (index) {
-            prof_begin(st, "memcpy(index)");
-            MSDA_CUDA(cudaMemcpyAsync(p.bin_off, index, table_bytes, cudaMemcpyDeviceToDevice, st));
-            prof_end(st);
-            ++g_launches;
+            // read-only from here on: the sort and the walker only look offsets up
+            p.bin_off = const_cast<uint32_t*>(static_cast<const uint32_t*>(index));
         } else {
             prof_begin(st, "memset(bin table)");
             MSDA_CUDA(cudaMemsetAsync(p.bin_off, 0, table_bytes, st));

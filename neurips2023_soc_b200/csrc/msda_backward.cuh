@@ -613,8 +613,12 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
     return e;
 }
 
+#ifndef MSDA_WALK_MIN_BLOCKS
+#define MSDA_WALK_MIN_BLOCKS 5
+#endif
+
 template <typename T, int VEC, int G>
-__global__ void __launch_bounds__(kGThreads) msda_grad_value_walk_kernel(const Params p) {
+__global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_value_walk_kernel(const Params p) {
     constexpr int D = VEC * G;
     constexpr int NGRP = kGThreads / G;          // groups per CTA
     constexpr int GW = 32 / G;                   // groups per warp

@@ -277,3 +277,27 @@ def test_error_behaviour():
     out = msda_ext.ms_deform_attn_forward(d.value, d.spatial_shapes, d.level_start_index, d.sampling_locations,
                                           d.attention_weights, 3)
     assert out.shape == (3, 4, 64) and msda_ext.last_launch_count() == 1
+
+
+def test_cuda_graph_capture_and_replay():
+    """Every launch of a forward + backward is asynchronous on the caller's stream with no hidden
+    synchronisation, so the pair can be captured once and replayed."""
+    x = make_inputs(N=2, dist="encoder", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], seed=11).to(DEV)
+    args = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
+    eager_out, index = msda_ext.ms_deform_attn_forward(*args, 64, want_index=True)
+    eager = msda_ext.ms_deform_attn_backward(*args, x.grad_output, 64, index=index)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            out, idx = msda_ext.ms_deform_attn_forward(*args, 64, want_index=True)
+            grads = msda_ext.ms_deform_attn_backward(*args, x.grad_output, 64, index=idx)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager_out)
+    for a, b in zip(grads, eager):
+        assert torch.equal(a, b)
