@@ -456,18 +456,21 @@ __device__ __forceinline__ void sort_in_lanes(Entry<CT>* base, const uint32_t cn
     }
     uint32_t key = w[0];          // Entry::id is the first word; empty lanes hold +inf
     int src = sub;
-#pragma unroll
-    for (int k = 2; k <= WIDTH; k <<= 1) {
-#pragma unroll
-        for (int j = k - 1; j > 0; j = (j == k - 1) ? (k >> 2) : (j >> 1)) {
-            const uint32_t ok = __shfl_xor_sync(mask, key, j, WIDTH);
-            const int os = __shfl_xor_sync(mask, src, j, WIDTH);
-            const bool lower = (sub & ((j == k - 1) ? (k >> 1) : j)) == 0;
-            const bool take = lower ? (ok < key) : (ok > key);
-            if (take) { key = ok; src = os; }
-            if (j == 1 || (j == k - 1 && k == 2)) break;
-        }
-    }
+    // one compare-exchange step of the network: partner = sub ^ J inside a merge of width K
+    auto step = [&](const int K, const int J) {
+        const uint32_t ok = __shfl_xor_sync(mask, key, J, WIDTH);
+        const int os = __shfl_xor_sync(mask, src, J, WIDTH);
+        const bool lower = (sub & ((J == K - 1) ? (K >> 1) : J)) == 0;
+        const bool take = lower ? (ok < key) : (ok > key);
+        key = take ? ok : key;
+        src = take ? os : src;
+    };
+    step(2, 1);
+    step(4, 3); step(4, 1);
+    step(8, 7); step(8, 2); step(8, 1);
+    if constexpr (WIDTH >= 16) { step(16, 15); step(16, 4); step(16, 2); step(16, 1); }
+    if constexpr (WIDTH >= 32) { step(32, 31); step(32, 8); step(32, 4); step(32, 2); step(32, 1); }
+    static_assert(WIDTH == 8 || WIDTH == 16 || WIDTH == 32, "network written out for 8, 16 and 32 lanes");
     // position `sub` receives the entry that lane `src` loaded
     uint32_t o[NW];
 #pragma unroll
