@@ -301,3 +301,87 @@ def test_cuda_graph_capture_and_replay():
     assert torch.equal(out, eager_out)
     for a, b in zip(grads, eager):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------- odd geometries
+def _check_against_oracle(x, vdt=torch.float32, adt=torch.float32, tol=1e-5, flags=0):
+    out, gv, gl, ga, (v, lo, at, go) = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                               x.attention_weights, x.grad_output, vdt, adt, flags=flags)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    keep = off_lattice(lo.double().cpu().numpy(), x.spatial_shapes.numpy(), 1e-3)
+    assert rel_err(out, r_out) <= tol
+    assert rel_err(gv, r_gv) <= tol
+    assert rel_err(ga, r_ga) <= tol
+    assert rel_err(gl, r_gl, keep) <= 2 * tol
+
+
+def test_level_start_index_with_gaps():
+    """value rows that belong to no level (level_start_index leaves gaps) take part in nothing and must
+    get an exactly zero gradient."""
+    x = make_inputs(N=2, dist="uniform", shapes=[(5, 6), (3, 4)], M=4, D=32, Lq=40, seed=31)
+    S2 = 30 + 7 + 12 + 5                                  # 7 unused rows between the levels, 5 at the end
+    value = torch.randn(2, S2, 4, 32, generator=torch.Generator().manual_seed(1))
+    x.value = value
+    x.level_start_index = torch.tensor([0, 37], dtype=torch.long)
+    out, gv, gl, ga, (v, lo, at, go) = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                               x.attention_weights, x.grad_output, torch.float32, torch.float32)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    assert rel_err(out, r_out) <= 1e-5 and rel_err(gv, r_gv) <= 1e-5 and rel_err(ga, r_ga) <= 1e-5
+    assert float(gv[:, 30:37].abs().max()) == 0.0 and float(gv[:, 49:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kw", [
+    dict(N=1, shapes=[(1, 1)], M=1, D=32, Lq=3, P=4, dist="uniform"),                       # a single pixel
+    dict(N=1, shapes=[(1, 37), (23, 1)], M=2, D=32, Lq=50, P=4, dist="uniform"),            # 1-pixel-wide maps
+    dict(N=3, shapes=[(2, 2)] * 16, M=2, D=32, Lq=9, P=4, dist="uniform"),                  # 16 levels
+    dict(N=1, shapes=[(40, 64), (20, 32)], M=1, D=64, Lq=700, P=8, dist="uniform"),         # P = 8, D = 64
+    dict(N=2, shapes=[(9, 11)], M=3, D=16, Lq=130, P=4, dist="uniform"),                    # D = 16, one level
+    dict(N=1, shapes=[(6, 7), (3, 4)], M=2, D=32, Lq=257, P=16, dist="uniform"),            # P = 16 (generic path)
+])
+def test_odd_geometries_fp32(kw):
+    _check_against_oracle(make_inputs(seed=41, **kw))
+
+
+def test_everything_out_of_range_and_nan_locations():
+    """No accepted sample at all: outputs and every gradient are exactly zero (cuh:288,365-374), also for
+    NaN locations, which no comparison accepts."""
+    x = make_inputs(N=1, dist="uniform", shapes=[(6, 8), (3, 4)], M=2, D=32, Lq=40, seed=51)
+    loc = x.sampling_locations * 0 + 3.0
+    loc[:, ::2] = float("nan")
+    out, gv, gl, ga, _ = run_op(x.value, x.spatial_shapes, x.level_start_index, loc, x.attention_weights,
+                                x.grad_output, torch.float32, torch.float32)
+    for t in (out, gv, gl, ga):
+        assert float(t.abs().max()) == 0.0
+
+
+def test_non_finite_values_stay_local():
+    """An Inf in one value row reaches only the outputs whose accepted corners touch it, exactly as in the
+    reference (rejected samples and corners outside the map read nothing)."""
+    x = make_inputs(N=1, dist="uniform", shapes=[(8, 8)], M=1, D=32, Lq=64, P=4, seed=61)
+    value = x.value.clone()
+    value[0, 27] = float("inf")                            # pixel (3, 3)
+    dev = x.to(DEV)
+    out = msda_ext.ms_deform_attn_forward(value.to(DEV), dev.spatial_shapes, dev.level_start_index,
+                                          dev.sampling_locations, dev.attention_weights, 64)
+    ref = O.forward_c(value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
+                      dtype=np.float32)
+    got = out.cpu().numpy()
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref.reshape(got.shape)))
+
+
+def test_large_query_count_and_frames():
+    """Config 4 / 5 sizes: 36 frames, and 20 k tokens per frame (one frame), forward + backward vs the
+    grid_sample formulation on the GPU."""
+    for kw in (dict(N=36, dist="decoder", Lq=5), dict(N=1, dist="encoder", shapes=[(96, 160), (48, 80), (24, 40), (12, 20)])):
+        x = make_inputs(seed=71, **kw).to(DEV)
+        out = msda_ext.ms_deform_attn_forward(x.value, x.spatial_shapes, x.level_start_index,
+                                              x.sampling_locations, x.attention_weights, 64)
+        gv, gl, ga = msda_ext.ms_deform_attn_backward(x.value, x.spatial_shapes, x.level_start_index,
+                                                      x.sampling_locations, x.attention_weights, x.grad_output, 64)
+        ref = O.grid_sample_port_grads(x.value, x.spatial_shapes.cpu(), x.sampling_locations, x.attention_weights,
+                                       x.grad_output)
+        keep = off_lattice(x.sampling_locations.cpu().numpy(), x.spatial_shapes.cpu().numpy(), 1e-3)
+        assert rel_err(out, ref[0].double().cpu().numpy()) <= 1e-5
+        assert rel_err(gv, ref[1].double().cpu().numpy()) <= 2e-5
+        assert rel_err(ga, ref[3].double().cpu().numpy()) <= 1e-5
+        assert rel_err(gl, ref[2].double().cpu().numpy(), keep) <= 5e-5
