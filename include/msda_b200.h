@@ -120,6 +120,22 @@ int msda_backward_indexed(const void *value, const int64_t *spatial_shapes, cons
                           int N, int S, int M, int D, int L, int Lq, int P,
                           int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
 
+/* Forward with the module's elementwise prologue fused in
+ * (/root/reference/models/ops/modules/ms_deform_attn.py:99-106, 2-d reference points):
+ *   attn_weight  = softmax over the L*P logits of every (query, head)
+ *   sampling_loc = reference_points[n][q][l] + sampling_offsets / (W_l, H_l)
+ * reference_points [N][Lq][L][2] fp32; sampling_offsets [N][Lq][M][L][P][2] and attn_logits
+ * [N][Lq][M][L*P] in in_dtype (the value dtype or F32); the two results are written as fp32 to
+ * sampling_loc_out / attn_weight_out (the module returns them, the backward reads them).
+ * Tile-kernel shapes with L*P <= 16 only: anything else returns MSDA_ERR_UNSUPPORTED and the caller
+ * keeps the unfused sequence.  `index` as in msda_forward_indexed (may be NULL). */
+int msda_forward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                       void *output, void *sampling_loc_out, void *attn_weight_out,
+                       void *index, size_t index_bytes,
+                       int N, int S, int M, int D, int L, int Lq, int P,
+                       int value_dtype, int in_dtype, int im2col_step, void *cuda_stream, unsigned flags);
+
 /* Bytes of device scratch msda_backward needs for this problem size. */
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P,
                                      int value_dtype, int aux_dtype);

@@ -12,8 +12,8 @@ The kernels live in ``csrc/`` and are reached through the C ABI in ``include/msd
 (``libmsda_b200.so``).  There is no CPU or PyTorch fallback: without the library, or on CPU
 tensors, calls raise.
 """
-from .functions import MSDeformAttnFunction
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 from .modules import MSDeformAttn
 
-__all__ = ["MSDeformAttnFunction", "MSDeformAttn"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MSDeformAttn"]
 __version__ = "0.1.0"

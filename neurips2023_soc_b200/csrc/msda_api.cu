@@ -190,6 +190,21 @@ int launch_fwd_tile(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
+    if (p.loc_out) {   // fused prologue: softmax + sampling locations computed in the staging threads
+        if (p.bin_off) {
+            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true, true>;
+            prof_begin(st, "msda_fwd_tile_kernel<fused>");
+            k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+            prof_end(st);
+        } else {
+            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false, true>;
+            prof_begin(st, "msda_fwd_tile_kernel<fused>");
+            k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+            prof_end(st);
+        }
+        MSDA_LAUNCHED("msda_fwd_tile_kernel<fused>");
+        return MSDA_OK;
+    }
     if (p.bin_off) {   // a backward will follow: count the sub-bin populations on the way
         auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true>;
         prof_begin(st, "msda_fwd_tile_kernel");
@@ -505,11 +520,18 @@ size_t msda_index_bytes(int N, int S, int M, int D, int L, int Lq, int P) {
     return index_bytes(N, S, M, L, Lq, P);
 }
 
-int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                         const void* sampling_loc, const void* attn_weight, void* output, void* index,
-                         size_t index_size, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
-                         int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
+static int forward_impl(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                        const void* sampling_loc, const void* attn_weight, void* output, void* index,
+                        size_t index_size, const void* reference_points, void* loc_out, void* attn_out, int N, int S,
+                        int M, int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
+                        void* cuda_stream, unsigned flags) {
     g_launches = 0;
+    const bool fused = reference_points != nullptr;
+    if (fused) {   // the raw offsets / logits may be bf16 next to fp32 values only through the value dtype rule below
+        if (!loc_out || !attn_out) return fail(MSDA_ERR_INVALID_ARGUMENT, "null sampling_loc / attn_weight output");
+        if (L * P > kSC)
+            return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue needs L*P <= %d, got %d", kSC, L * P);
+    }
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
     if (rc) return rc;
@@ -520,6 +542,8 @@ int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const
     memset(&p, 0, sizeof p);
     p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
     p.loc = sampling_loc; p.attn = attn_weight; p.out = output;
+    p.ref = static_cast<const float*>(reference_points);
+    p.loc_out = static_cast<float*>(loc_out); p.attn_out = static_cast<float*>(attn_out);
     p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = L * P;
     p.id_shift = id_shift_for(p.LP);
     p.flags = flags;
@@ -543,6 +567,8 @@ int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const
 
     const bool aux32 = aux_dtype == MSDA_F32;
     const bool tile = pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16);
+    if (fused && !(tile && aligned16(reference_points) && aligned16(loc_out) && aligned16(attn_out)))
+        return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue exists for the tile kernels only (fp32/bf16, D and P as in DESIGN.md)");
     switch (value_dtype) {
         case MSDA_F32:
             rc = tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st) : launch_fwd_generic<float, float, float>(p, st);
@@ -570,6 +596,26 @@ int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const
         case MSDA_F16: return launch_count_scan<__half, float>(p, count_now, st);
         default: return launch_count_scan<double, double>(p, count_now, st);
     }
+}
+
+int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const void* sampling_loc, const void* attn_weight, void* output, void* index,
+                         size_t index_size, int N, int S, int M, int D, int L, int Lq, int P, int value_dtype,
+                         int aux_dtype, int im2col_step, void* cuda_stream, unsigned flags) {
+    return forward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, index, index_size,
+                        nullptr, nullptr, nullptr, N, S, M, D, L, Lq, P, value_dtype, aux_dtype, im2col_step,
+                        cuda_stream, flags);
+}
+
+int msda_forward_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const void* reference_points, const void* sampling_offsets, const void* attn_logits,
+                       void* output, void* sampling_loc_out, void* attn_weight_out, void* index, size_t index_size,
+                       int N, int S, int M, int D, int L, int Lq, int P, int value_dtype, int in_dtype,
+                       int im2col_step, void* cuda_stream, unsigned flags) {
+    if (!reference_points) return fail(MSDA_ERR_INVALID_ARGUMENT, "null reference_points");
+    return forward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, output, index,
+                        index_size, reference_points, sampling_loc_out, attn_weight_out, N, S, M, D, L, Lq, P,
+                        value_dtype, in_dtype, im2col_step, cuda_stream, flags);
 }
 
 int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
     if (cur.t >= total_tiles) return;
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
-    stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
+    stage_load<TA, G, P>(st, p, &tm, tl, cur, loc, attn);
     stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, tl, cur, desc[0]);
     __syncthreads();
 
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         Tile ntl = tl;
         if (has_next) {
             if (nxt.t != cur.t) ntl = decode_tile(p, lv, &tm, nxt.t, tile_q);
-            stage_load<TA, G>(st, p, &tm, ntl, nxt, loc, attn);
+            stage_load<TA, G, P>(st, p, &tm, ntl, nxt, loc, attn);
         }
 
         const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);

@@ -36,6 +36,10 @@ struct Params {
     const void* loc;         // [N][Lq][M][L][P][2]
     const void* attn;        // [N][Lq][M][L][P]
     const void* grad_out;    // [N][Lq][M*D]           (backward)
+    // fused prologue (msda_tiles.cuh): loc/attn above then hold the raw sampling offsets / attention logits
+    const float* ref;        // [N][Lq][L][2] reference points
+    float* loc_out;          // [N][Lq][M][L][P][2]  sampling locations computed on the way
+    float* attn_out;         // [N][Lq][M][L][P]     softmax of the logits
     void* out;               // [N][Lq][M*D]           (forward)
     void* grad_value;        // [N][S][M][D]
     void* grad_loc;

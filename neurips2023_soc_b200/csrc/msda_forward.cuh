@@ -33,7 +33,9 @@ namespace msda {
 // T value dtype, TA location/weight dtype, VEC channels per lane, G = D / VEC lanes per row,
 // P points per level (compile time so that the per-level constants hoist out of the loop).
 // COUNT: also count the accepted samples per sub-bin for a backward that will follow.
-template <typename T, typename TA, int VEC, int G, int P, bool COUNT>
+// FUSED: the softmax / sampling-location prologue of MSDeformAttn.forward runs in the staging
+// threads (TA is then the dtype of the raw offsets / logits; the results are fp32).
+template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_kernel(const Params p, const int rounds) {
     constexpr int MODE = COUNT ? kIndexCount : kIndexNone;
     using TS = TileShape<G>;
@@ -64,8 +66,8 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
     if (cur.t >= total_tiles) return;
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
-    stage_load<TA, G>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, MODE>(st, p, lv, tl, cur, desc[0]);
+    stage_load<TA, G, P, FUSED>(st, p, &tm, tl, cur, loc, attn);
+    stage_build<G, P, MODE, FUSED>(st, p, lv, tl, cur, desc[0]);
     __syncthreads();
 
     int buf = 0;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
         Tile ntl = tl;
         if (has_next) {
             if (nxt.t != cur.t) ntl = decode_tile(p, lv, &tm, nxt.t, tile_q);
-            stage_load<TA, G>(st, p, &tm, ntl, nxt, loc, attn);      // HBM loads fly during the gather
+            stage_load<TA, G, P, FUSED>(st, p, &tm, ntl, nxt, loc, attn);      // HBM loads fly during the gather
         }
 
         const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
                 store_row<T, VEC>(out + (((size_t)tl.n * p.Lq + q_mine) * p.M + tl.m) * p.D + gl * VEC, acc);
         }
 
-        if (has_next) stage_build<G, P, MODE>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        if (has_next) stage_build<G, P, MODE, FUSED>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
         __syncthreads();
         if (!has_next) break;
         cur = nxt;

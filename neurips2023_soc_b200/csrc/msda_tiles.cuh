@@ -27,6 +27,7 @@ struct Work {
 template <int DPT>
 struct Staged {     // what a staging thread carries from prefetch to descriptor build
     float x[DPT], y[DPT], a[DPT];
+    float rx[DPT], ry[DPT];   // fused prologue only: the reference point of (query, level)
     int q[DPT];     // query index, -1: empty slot
 };
 
@@ -50,8 +51,9 @@ __device__ __forceinline__ Work next_work(const Work w, const int rounds, const 
     return n;
 }
 
-// Issue the global loads of one work item (no use of the results here).
-template <typename TA, int G>
+// Issue the global loads of one work item (no use of the results here).  FUSED: `loc` / `attn`
+// are the raw sampling offsets / attention logits and the reference point comes along.
+template <typename TA, int G, int P, bool FUSED = false>
 __device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const Params& p, const TileMap* tm,
                                            const Tile& tl, const Work& w, const TA* __restrict__ loc,
                                            const TA* __restrict__ attn) {
@@ -70,6 +72,47 @@ __device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const 
             const XY<float> xy = load_xy(loc + 2 * si);
             st.x[k] = xy.x; st.y[k] = xy.y;
             st.a[k] = Elem<TA>::to_f(__ldg(attn + si));
+            if constexpr (FUSED) {
+                const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) +
+                                       ((size_t)tl.n * p.Lq + q) * p.L + min(sg / P, p.L - 1));
+                st.rx[k] = r.x; st.ry[k] = r.y;
+            }
+        }
+    }
+}
+
+// Fused prologue of MSDeformAttn.forward (/root/reference/models/ops/modules/ms_deform_attn.py:99-106):
+//   attention_weights = softmax over the L*P logits of (query, head)
+//   sampling_location = reference_point[level] + offset / (W_level, H_level)
+// The 16 samples of one (query, head) sit in 16 consecutive staging lanes, so the softmax is two
+// 16-lane shuffle reductions.  Both results are also written out: the module returns them and the
+// backward reads them.  Requires L*P <= 16 (one chunk).
+template <int G, int P>
+__device__ __forceinline__ void fused_prologue(Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
+                                               const Tile& tl, const Work& w) {
+    constexpr int DPT = TileShape<G>::DPT;
+    const int st_s = threadIdx.x % kSC;
+    const int sg = w.c0 + st_s;
+    const Level L_ = lv[min(sg / P, p.L - 1)];
+    const uint32_t hmask = 0xffffu << (threadIdx.x & 16);
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const bool live = st.q[k] >= 0;                  // false for empty rows and for slots past L*P
+        if (__ballot_sync(hmask, live) == 0) continue;   // empty row: uniform over its 16 lanes
+        float m = live ? st.a[k] : -INFINITY;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(hmask, m, d, 16));
+        const float e = live ? expf(st.a[k] - m) : 0.f;
+        float sum = e;
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) sum += __shfl_xor_sync(hmask, sum, d, 16);
+        if (live) {
+            st.a[k] = e / sum;
+            st.x[k] = st.rx[k] + st.x[k] / (float)L_.W;
+            st.y[k] = st.ry[k] + st.y[k] / (float)L_.H;
+            const size_t si = (((size_t)tl.n * p.Lq + st.q[k]) * p.M + tl.m) * p.LP + sg;
+            reinterpret_cast<float2*>(p.loc_out)[si] = make_float2(st.x[k], st.y[k]);
+            p.attn_out[si] = st.a[k];
         }
     }
 }
@@ -85,10 +128,11 @@ __device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const 
 // floating-point result.
 constexpr int kIndexNone = 0, kIndexCount = 1, kIndexFill = 2;
 
-template <int G, int P, int MODE>
-__device__ __forceinline__ void stage_build(const Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
+template <int G, int P, int MODE, bool FUSED = false>
+__device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
                                             const Tile& tl, const Work& w, uint4* __restrict__ desc) {
     constexpr int DPT = TileShape<G>::DPT;
+    if constexpr (FUSED) fused_prologue<G, P>(st, p, lv, tl, w);
     const int st_s = threadIdx.x % kSC, st_j0 = threadIdx.x / kSC;
     const int sg = w.c0 + st_s;
     const int l = min(sg / P, p.L - 1);

@@ -57,3 +57,55 @@ class MSDeformAttnFunction(Function):
             index=ctx.index)
         ctx.index = None
         return grad_value, None, None, grad_loc.to(ctx.aux_in[0]), grad_attn.to(ctx.aux_in[1]), None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """The op together with the elementwise prologue of ``MSDeformAttn.forward``
+    (/root/reference/models/ops/modules/ms_deform_attn.py:99-106, 2-d reference points):
+
+        MSDeformAttnFusedFunction.apply(value, value_spatial_shapes, value_level_start_index,
+                                        reference_points, sampling_offsets, attention_logits, im2col_step)
+            -> (output, sampling_locations, attention_weights)
+
+    The forward kernel forms ``softmax(attention_logits)`` and ``reference_points + sampling_offsets / (W, H)``
+    in its staging threads (one pass over the raw projections instead of five elementwise kernels) and writes
+    both out in fp32, as autocast would produce them.  The backward runs the same kernels as
+    ``MSDeformAttnFunction`` on those saved tensors and applies the chain rule of the two elementwise maps.
+    Only for shapes ``msda_ext.fused_prologue_supported`` accepts.
+    """
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attention_logits, im2col_step):
+        ctx.im2col_step = im2col_step
+        ctx.in_dtypes = (sampling_offsets.dtype, attention_logits.dtype, reference_points.dtype)
+        raw = sampling_offsets.dtype if (sampling_offsets.dtype == attention_logits.dtype and
+                                         sampling_offsets.dtype in (value.dtype, torch.float32)) else torch.float32
+        value = value.contiguous()
+        want_index = any(ctx.needs_input_grad[i] for i in (0, 3, 4, 5))
+        res = msda_ext.ms_deform_attn_forward_fused(
+            value, value_spatial_shapes, value_level_start_index, reference_points.float().contiguous(),
+            sampling_offsets.to(raw).contiguous(), attention_logits.to(raw).contiguous(), im2col_step,
+            want_index=want_index)
+        output, loc, attn = res[:3]
+        ctx.index = res[3] if want_index else None
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, loc, attn)
+        return output, loc, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output, grad_loc_out, grad_attn_out):
+        value, shapes, lsi, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = msda_ext.ms_deform_attn_backward(
+            value, shapes, lsi, loc, attn, grad_output.to(value.dtype).contiguous(), ctx.im2col_step, index=ctx.index)
+        ctx.index = None
+        if grad_loc_out is not None:          # someone differentiated through the returned locations / weights
+            grad_loc = grad_loc + grad_loc_out
+        if grad_attn_out is not None:
+            grad_attn = grad_attn + grad_attn_out
+        wh = shapes.flip(-1).to(grad_loc.dtype)[None, None, None, :, None, :]
+        grad_offsets = (grad_loc / wh).to(ctx.in_dtypes[0])
+        grad_ref = grad_loc.sum(dim=(2, 4)).to(ctx.in_dtypes[2]) if ctx.needs_input_grad[3] else None
+        dot = (grad_attn * attn).sum(dim=(-1, -2), keepdim=True)
+        grad_logits = (attn * (grad_attn - dot)).flatten(-2).to(ctx.in_dtypes[1])
+        return grad_value, None, None, grad_ref, grad_offsets, grad_logits, None

@@ -25,7 +25,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions import MSDeformAttnFunction
+from .. import msda_ext
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _power_of_two(n: int) -> bool:
@@ -44,6 +45,8 @@ class MSDeformAttn(nn.Module):
                           "for bf16) takes the 128-bit tile kernels; other sizes use the generic kernels.")
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        #: run softmax + location arithmetic inside the forward kernel when a kernel exists for the shape
+        self.fused_prologue = True
 
         samples = n_heads * n_levels * n_points
         self.sampling_offsets = nn.Linear(d_model, 2 * samples)
@@ -86,9 +89,16 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, S, M, self.d_model // M)
 
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        logits = self.attention_weights(query).view(N, Lq, M, L * P)
 
         box = reference_points.shape[-1]
+        if self.fused_prologue and msda_ext.fused_prologue_supported(value, L, P, box):
+            output, sampling_locations, weights = MSDeformAttnFusedFunction.apply(
+                value, input_spatial_shapes, input_level_start_index, reference_points, offsets, logits,
+                self.im2col_step)
+            return self.output_proj(output), sampling_locations, weights
+
+        weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         if box == 2:
             # offsets are in pixels of each level: divide by (W_l, H_l)
             wh = input_spatial_shapes.flip(-1)

@@ -119,5 +119,51 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
+def fused_prologue_supported(value, n_levels: int, n_points: int, ref_dim: int) -> bool:
+    """Whether ms_deform_attn_forward_fused has a kernel for this call: tile-kernel
+    shapes (fp32 rows of 64/128/256 B, bf16 rows of 64/128/256 B, P in {4, 8}), L*P <= 16, 2-d reference
+    points.  Anything else keeps the unfused sequence."""
+    if not value.is_cuda or ref_dim != 2 or n_levels * n_points > 16 or n_points not in (4, 8):
+        return False
+    row = value.shape[-1] * value.element_size()
+    return value.dtype in (torch.float32, torch.bfloat16) and row in (64, 128, 256)
+
+
+def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attn_logits, im2col_step: int, flags: int | None = None, want_index: bool = False):
+    """Forward with the module's prologue fused in (msda_forward_fused): returns
+    ``(output, sampling_locations fp32, attention_weights fp32[, index])``."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
+                   ("attn_logits", attn_logits)])
+    _require(value.dim() == 4 and sampling_offsets.dim() == 6 and sampling_offsets.shape[-1] == 2, "bad shapes")
+    N, S, M, D = value.shape
+    _, Lq, M2, L, P, _ = sampling_offsets.shape
+    _require(M2 == M and spatial_shapes.shape[0] == L and attn_logits.numel() == N * Lq * M * L * P,
+             "sampling_offsets / attn_logits do not match value / spatial_shapes")
+    _require(tuple(reference_points.shape) == (N, Lq, L, 2) and reference_points.dtype == torch.float32,
+             "reference_points must be fp32 (N, Lq, L, 2)")
+    _require(sampling_offsets.dtype == attn_logits.dtype and
+             (sampling_offsets.dtype == value.dtype or sampling_offsets.dtype == torch.float32),
+             "sampling_offsets / attn_logits must share a dtype: the value dtype or float32")
+    dims = (N, S, M, D, L, Lq, P)
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        loc = torch.empty((N, Lq, M, L, P, 2), dtype=torch.float32, device=value.device)
+        attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device)
+        index, index_ptr, index_bytes = None, None, 0
+        if want_index:
+            index_bytes = int(lib.msda_index_bytes(*dims))
+            index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
+            index_ptr = index.data_ptr()
+        _lib.check(lib.msda_forward_fused(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+            index_ptr, index_bytes, *dims, _DTYPE[value.dtype], _DTYPE[sampling_offsets.dtype], int(im2col_step),
+            torch.cuda.current_stream().cuda_stream, DEFAULT_FLAGS if flags is None else flags))
+    return (out, loc, attn, index) if want_index else (out, loc, attn)
+
+
 def last_launch_count() -> int:
     return int(_lib.load().msda_last_launch_count())

@@ -385,3 +385,58 @@ def test_large_query_count_and_frames():
         assert rel_err(gv, ref[1].double().cpu().numpy()) <= 2e-5
         assert rel_err(ga, ref[3].double().cpu().numpy()) <= 1e-5
         assert rel_err(gl, ref[2].double().cpu().numpy(), keep) <= 5e-5
+
+
+# ---------------------------------------------------------------------------- module level
+@pytest.mark.parametrize("amp", [False, True])
+def test_module_fused_prologue_matches_unfused(amp):
+    """MSDeformAttn with softmax + location arithmetic fused into the forward kernel against the same module
+    running the reference's elementwise sequence (ms_deform_attn.py:99-106) around the plain op: outputs,
+    returned locations / weights and every parameter and input gradient."""
+    from neurips2023_soc_b200 import MSDeformAttn
+    torch.manual_seed(0)
+    shapes_l = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in shapes_l)
+    shapes = torch.tensor(shapes_l, dtype=torch.long, device=DEV)
+    lsi = torch.tensor([0, 240, 300, 315], dtype=torch.long, device=DEV)
+    mod = MSDeformAttn(256, 4, 8, 4).to(DEV)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.2)
+    N, Lq = 2, 37
+    query = torch.randn(N, Lq, 256, device=DEV, requires_grad=True)
+    src = torch.randn(N, S, 256, device=DEV, requires_grad=True)
+    ref = torch.rand(N, Lq, 4, 2, device=DEV, requires_grad=True)
+    pad = torch.zeros(N, S, dtype=torch.bool, device=DEV)
+    pad[1, -9:] = True
+    g = torch.randn(N, Lq, 256, device=DEV)
+
+    def run(fused):
+        mod.fused_prologue = fused
+        for t in (query, src, ref):
+            t.grad = None
+        mod.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            if fused:
+                out, loc, w = mod(query, ref, src, shapes, lsi, pad)
+            else:
+                # the reference's sequence with the elementwise part evaluated in fp32 from the same
+                # (possibly bf16) projections -- under autocast the stock sequence rounds offset / (W, H)
+                # to bf16 first, which moves samples across pixel borders and makes grad_loc incomparable
+                value = mod.value_proj(src).masked_fill(pad[..., None], 0.0).view(N, S, 8, 32)
+                off = mod.sampling_offsets(query).view(N, Lq, 8, 4, 4, 2).float()
+                w = torch.softmax(mod.attention_weights(query).view(N, Lq, 8, 16).float(), -1).view(N, Lq, 8, 4, 4)
+                loc = ref[:, :, None, :, None, :] + off / shapes.flip(-1)[None, None, None, :, None, :]
+                out = mod.output_proj(MSDeformAttnFunction.apply(value, shapes, lsi, loc, w, 64))
+        (out.float() * g).sum().backward()
+        grads = [p.grad.clone() for p in mod.parameters()] + [query.grad.clone(), src.grad.clone(), ref.grad.clone()]
+        return out.detach().float(), loc.detach().float(), w.detach().float(), grads
+
+    a, b = run(True), run(False)
+    tol = 3e-2 if amp else 2e-5
+    assert a[1].dtype == torch.float32 and a[1].shape == (N, Lq, 8, 4, 4, 2)
+    assert float((a[1] - b[1]).abs().max()) <= 1e-6                          # sampling locations
+    assert float((a[2] - b[2]).abs().max()) <= 1e-6                          # attention weights
+    assert float((a[0] - b[0]).abs().max()) <= tol * max(1.0, float(b[0].abs().max()))
+    for x, y in zip(a[3], b[3]):
+        assert float((x.float() - y.float()).abs().max()) <= tol * max(1.0, float(y.float().abs().max()))
