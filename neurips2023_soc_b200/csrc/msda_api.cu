@@ -305,13 +305,12 @@ int launch_fill(const Params& p, cudaStream_t st) {
 
 template <typename CT>
 int launch_sort(const Params& p, cudaStream_t st) {
-    const long long spans = (long long)p.N * p.M * ceil_div(p.sb_max, 32);
-    const long long sb = ceil_div(spans, kThreads / 32);
-    const long long scap = (long long)num_sms() * 8;
-    prof_begin(st, "msda_bin_sort_small_kernel");
-    msda_bin_sort_small_kernel<CT><<<(int)(sb < scap ? sb : scap), kThreads, 0, st>>>(p);
+    auto k = msda_bin_rank_sort_kernel<CT>;
+    const long long items = (long long)p.N * p.M * ceil_div(p.sb_max, kRankSpan);
+    prof_begin(st, "msda_bin_rank_sort_kernel");
+    k<<<persistent_grid(k, kThreads, items), kThreads, 0, st>>>(p);
     prof_end(st);
-    MSDA_LAUNCHED("msda_bin_sort_small_kernel");
+    MSDA_LAUNCHED("msda_bin_rank_sort_kernel");
     prof_begin(st, "msda_bin_sort_big_kernel");
     msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
     prof_end(st);
@@ -423,7 +422,7 @@ WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
     WsLayout w;
     const size_t samples = (size_t)N * Lq * M * L * P;
     w.sb_max = sub_bin_bound(S, L, Lq, P);
-    w.big_cap = (int)(samples / (kBigBin + 1) + 1);
+    w.big_cap = (int)(samples / (kRankMax + 1) + 1);
     const size_t entry = vdt == MSDA_F64 ? sizeof(Entry<double>) : sizeof(Entry<float>);
     const size_t table = index_bytes(N, S, M, L, Lq, P);
     w.bin_off = 0;

@@ -27,8 +27,9 @@
 //                integer addition commutes, so counts are exact and order-free)
 //        scan  : per (frame, head) exclusive scan of the bin counts
 //        fill  : every sample writes a 16-byte entry {query|sample id, lh, lw, a}
-//        sort  : each bin's entries are put in ascending id order, which makes the
-//                summation order below a pure function of the inputs
+//        sort  : each sub-bin's entries are put in ascending id order (every entry counts the
+//                smaller ids of its sub-bin), which makes the summation order below a pure
+//                function of the inputs
 //        gather: a group of G lanes owns one grad_value row (pixel, head); the pixel is
 //                corner 1/2/3/4 of the samples binned at (y+1,x+1)/(y+1,x)/(y,x+1)/(y,x);
 //                it walks those four lists in order, accumulates
@@ -41,7 +42,6 @@
 
 namespace msda {
 
-constexpr int kBigBin = 32;  // bins with more entries are sorted by msda_bin_sort_big_kernel
 
 template <typename CT> struct Entry;
 template <> struct __align__(16) Entry<float> {
@@ -435,105 +435,99 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
 }
 
 // ---- sort ---------------------------------------------------------------------------
-// All compare-exchanges are ascending (lower index keeps the smaller id); each merge
-// starts with a mirror step (partner = i ^ (k-1)) followed by half-cleaners
-// (partner = i ^ j).  Missing elements (index >= cnt) act as +inf and never move.
+// Every sub-bin is put in ascending id order, in place.  A CTA stages a run of consecutive
+// sub-bins (their entries are contiguous) in shared memory; then every ENTRY finds its own rank
+// inside its sub-bin by counting the smaller ids (a handful of shared-memory reads: sub-bins hold
+// about six entries) and is written back to `first slot + rank`.  All lanes do the same amount
+// of work whatever the sub-bin sizes are.  Sub-bins with more than kRankMax entries go to the
+// big list instead (msda_bin_sort_big_kernel: bitonic network, one CTA per sub-bin).
+constexpr int kRankSpan = 256;   // sub-bins staged per step (at most)
+constexpr int kRankMax = 512;    // largest sub-bin ranked by counting
 
-template <typename CT, int WIDTH>
-__device__ __forceinline__ void sort_in_lanes(Entry<CT>* base, const uint32_t cnt, const int sub, const uint32_t mask) {
-    // `sub` = lane index inside a WIDTH-lane segment; one entry per lane, read once.
-    constexpr int NW = sizeof(Entry<CT>) / 4;
-    uint32_t w[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) w[i] = 0xffffffffu;
-    if (sub < (int)cnt) {
-        const uint4* src4 = reinterpret_cast<const uint4*>(base + sub);
-#pragma unroll
-        for (int i = 0; i < NW / 4; ++i) {
-            const uint4 t = src4[i];
-            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-        }
-    }
-    uint32_t key = w[0];          // Entry::id is the first word; empty lanes hold +inf
-    int src = sub;
-    // one compare-exchange step of the network: partner = sub ^ J inside a merge of width K
-    auto step = [&](const int K, const int J) {
-        const uint32_t ok = __shfl_xor_sync(mask, key, J, WIDTH);
-        const int os = __shfl_xor_sync(mask, src, J, WIDTH);
-        const bool lower = (sub & ((J == K - 1) ? (K >> 1) : J)) == 0;
-        const bool take = lower ? (ok < key) : (ok > key);
-        key = take ? ok : key;
-        src = take ? os : src;
-    };
-    step(2, 1);
-    step(4, 3); step(4, 1);
-    step(8, 7); step(8, 2); step(8, 1);
-    if constexpr (WIDTH >= 16) { step(16, 15); step(16, 4); step(16, 2); step(16, 1); }
-    if constexpr (WIDTH >= 32) { step(32, 31); step(32, 8); step(32, 4); step(32, 2); step(32, 1); }
-    static_assert(WIDTH == 8 || WIDTH == 16 || WIDTH == 32, "network written out for 8, 16 and 32 lanes");
-    // position `sub` receives the entry that lane `src` loaded
-    uint32_t o[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) o[i] = __shfl_sync(mask, w[i], src, WIDTH);
-    if (sub < (int)cnt) {
-        uint4* dst4 = reinterpret_cast<uint4*>(base + sub);
-#pragma unroll
-        for (int i = 0; i < NW / 4; ++i) dst4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-    }
-}
-
-// Sub-bins of up to 32 entries, sorted in place.  A warp takes 32 consecutive sub-bins: their
-// offsets are read with one coalesced load and handed around with shuffles; sub-bins of 2..8
-// entries are sorted four at a time by the warp's 8-lane segments, those of 9..32 by the
-// whole warp.
 template <typename CT>
-__global__ void __launch_bounds__(kThreads) msda_bin_sort_small_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads) msda_bin_rank_sort_kernel(const Params p) {
+    constexpr int CAP = 32768 / (int)sizeof(Entry<CT>);     // entries staged per step
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
+    __shared__ Entry<CT> buf[CAP];
+    __shared__ uint32_t ids[CAP];
+    __shared__ uint16_t owner[CAP];
+    __shared__ uint32_t soff[kRankSpan + 1];
+    __shared__ int s_take;
     load_levels(p, lv, &s_sb, &s_sq);
     Entry<CT>* __restrict__ entries = static_cast<Entry<CT>*>(p.entries);
     const int SB = s_sb;
     const size_t per_nm = (size_t)p.Lq * p.LP;
-    const int lane = threadIdx.x & 31, sub = lane & 7, seg = lane >> 3;
-    const uint32_t segmask = 0xffu << (lane & 24);
-    const int spans = (SB + 31) / 32;                      // 32-sub-bin spans per (frame, head)
-    const size_t total = (size_t)p.N * p.M * spans;
-    const size_t warps = (size_t)gridDim.x * (kThreads / 32);
-    for (size_t w = (size_t)blockIdx.x * (kThreads / 32) + threadIdx.x / 32; w < total; w += warps) {
-        const size_t nm = w / spans;
-        const int b = (int)(w - nm * spans) * 32 + lane;
-        const uint32_t* off = p.bin_off + nm * (p.sb_max + 1);
-        uint32_t beg = 0, cnt = 0;
-        if (b < SB) {
-            beg = off[b];
-            cnt = off[b + 1] - beg;
-        }
-        Entry<CT>* ent = entries + nm * per_nm;
-        if (cnt > (uint32_t)kBigBin) {              // left to msda_bin_sort_big_kernel
-            const uint32_t k = atomicAdd(p.counts, 1u);
-            if (k < (uint32_t)p.big_cap) {
-                p.big_bins[2 * k] = (uint32_t)nm;
-                p.big_bins[2 * k + 1] = (uint32_t)b;
+    const int spans = (SB + kRankSpan - 1) / kRankSpan;
+    const int total = p.N * p.M * spans;
+    const int tid = threadIdx.x;
+
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int nm = item / spans;
+        const int b_end = min(SB, (item - nm * spans + 1) * kRankSpan);
+        const uint32_t* off = p.bin_off + (size_t)nm * (p.sb_max + 1);
+        Entry<CT>* ent = entries + (size_t)nm * per_nm;
+        int b = (item - nm * spans) * kRankSpan;
+        while (b < b_end) {
+            const int n = min(kRankSpan, b_end - b);
+            for (int i = tid; i <= n; i += kThreads) soff[i] = off[b + i];
+            __syncthreads();
+            if (tid == 0) {
+                // as many whole sub-bins as fit the staging buffer (at least one)
+                int lo = 1, hi = n;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (soff[mid] - soff[0] <= (uint32_t)CAP) lo = mid; else hi = mid - 1;
+                }
+                s_take = lo;
             }
-        }
-#pragma unroll 4
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t sbeg = __shfl_sync(0xffffffffu, beg, seg * 8 + j);
-            const uint32_t scnt = __shfl_sync(0xffffffffu, cnt, seg * 8 + j);
-            if (scnt >= 2 && scnt <= 8) sort_in_lanes<CT, 8>(ent + sbeg, scnt, sub, segmask);
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, cnt > 8 && cnt <= (uint32_t)kBigBin);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t bbeg = __shfl_sync(0xffffffffu, beg, src);
-            const uint32_t bcnt = __shfl_sync(0xffffffffu, cnt, src);
-            sort_in_lanes<CT, 32>(ent + bbeg, bcnt, lane, 0xffffffffu);
+            __syncthreads();
+            const int take = s_take;
+            const uint32_t base = soff[0];
+            const uint32_t cnt_e = soff[take] - base;
+            if (cnt_e <= (uint32_t)CAP) {
+                for (uint32_t e = tid; e < cnt_e; e += kThreads) {
+                    const Entry<CT> t = ent[base + e];
+                    buf[e] = t;
+                    ids[e] = t.id;
+                }
+                for (int i = tid; i < take; i += kThreads) {
+                    const uint32_t lo = soff[i] - base, hi = soff[i + 1] - base;
+                    if (hi - lo > (uint32_t)kRankMax) {
+                        const uint32_t k = atomicAdd(p.counts, 1u);
+                        if (k < (uint32_t)p.big_cap) {
+                            p.big_bins[2 * k] = (uint32_t)nm;
+                            p.big_bins[2 * k + 1] = (uint32_t)(b + i);
+                        }
+                    }
+                    for (uint32_t e = lo; e < hi; ++e) owner[e] = (uint16_t)i;
+                }
+                __syncthreads();
+                for (uint32_t e = tid; e < cnt_e; e += kThreads) {
+                    const int i = owner[e];
+                    const uint32_t lo = soff[i] - base, hi = soff[i + 1] - base;
+                    const uint32_t c = hi - lo;
+                    if (c >= 2 && c <= (uint32_t)kRankMax) {
+                        const uint32_t key = ids[e];
+                        uint32_t r = 0;
+                        for (uint32_t j = lo; j < hi; ++j) r += ids[j] < key;
+                        if (lo + r != e) ent[base + lo + r] = buf[e];
+                    }
+                }
+            } else if (tid == 0) {          // a single sub-bin larger than the buffer
+                const uint32_t k = atomicAdd(p.counts, 1u);
+                if (k < (uint32_t)p.big_cap) {
+                    p.big_bins[2 * k] = (uint32_t)nm;
+                    p.big_bins[2 * k + 1] = (uint32_t)b;
+                }
+            }
+            __syncthreads();
+            b += take;
         }
     }
 }
 
-// Bins with more than kBigBin entries: one CTA per bin, bitonic network over a
+// Sub-bins with more than kRankMax entries: one CTA per sub-bin, bitonic network over a
 // shared-memory copy (or in place in global memory when the bin does not fit).
 template <typename CT>
 __global__ void __launch_bounds__(kThreads) msda_bin_sort_big_kernel(const Params p) {

@@ -45,8 +45,11 @@ class MSDeformAttn(nn.Module):
                           "for bf16) takes the 128-bit tile kernels; other sizes use the generic kernels.")
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
-        #: run softmax + location arithmetic inside the forward kernel when a kernel exists for the shape
-        self.fused_prologue = True
+        #: True: run softmax + location arithmetic inside the forward kernel when a kernel exists for the
+        #: shape (MSDeformAttnFusedFunction).  Opt-in: measured neutral at the encoder level this round (the
+        #: heavier staging of the forward kernel costs what the three elementwise kernels it replaces cost);
+        #: it does keep offset / (W, H) in fp32 under autocast, where the stock sequence rounds it to bf16.
+        self.fused_prologue = False
 
         samples = n_heads * n_levels * n_points
         self.sampling_offsets = nn.Linear(d_model, 2 * samples)

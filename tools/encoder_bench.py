@@ -56,7 +56,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--amp", action="store_true")
-    ap.add_argument("--no-fuse", action="store_true", help="keep softmax / location arithmetic in PyTorch")
+    ap.add_argument("--fuse", action="store_true", help="softmax / location arithmetic inside the forward kernel")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -76,7 +76,7 @@ def main():
     with torch.no_grad():          # leave the all-zero init of the offset / attention projections
         for m in model.modules():
             if isinstance(m, MSDeformAttn):
-                m.fused_prologue = not a.no_fuse
+                m.fused_prologue = a.fuse
                 m.sampling_offsets.weight.normal_(0, 0.02)
                 m.attention_weights.weight.normal_(0, 0.02)
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
@@ -114,7 +114,7 @@ def main():
     _lib.profile_enable(False)
     if rank == 0:
         print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "layers": a.layers, "frames_per_gpu": a.frames,
-                          "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": not a.no_fuse, "n_gpus": world, "ms_per_step": float(ms.item()),
+                          "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "n_gpus": world, "ms_per_step": float(ms.item()),
                           "queries_per_s": world * a.frames * S / (float(ms.item()) * 1e-3),
                           "msda_forward_kernels_ms": fwd_ms, "loss": float(loss)}))
     if world > 1:
