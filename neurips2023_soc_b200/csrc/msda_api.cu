@@ -185,40 +185,42 @@ int persistent_grid(K kernel, int threads, long long work_items) {
 
 // ------------------------------------------------------------------------------------------
 // forward
-template <typename T, typename TA, int VEC, int G, int P>
-int launch_fwd_tile(const Params& p, cudaStream_t st) {
+template <typename T, typename TA, int VEC, int G, int P, int ROWB>
+int launch_fwd_tile_rowb(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
+    const char* name = p.loc_out ? "msda_fwd_tile_kernel<fused>" : "msda_fwd_tile_kernel";
+    prof_begin(st, name);
     if (p.loc_out) {   // fused prologue: softmax + sampling locations computed in the staging threads
         if (p.bin_off) {
-            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true, true>;
-            prof_begin(st, "msda_fwd_tile_kernel<fused>");
+            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true, true, ROWB>;
             k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
-            prof_end(st);
         } else {
-            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false, true>;
-            prof_begin(st, "msda_fwd_tile_kernel<fused>");
+            auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false, true, ROWB>;
             k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
-            prof_end(st);
         }
-        MSDA_LAUNCHED("msda_fwd_tile_kernel<fused>");
-        return MSDA_OK;
-    }
-    if (p.bin_off) {   // a backward will follow: count the sub-bin populations on the way
-        auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true>;
-        prof_begin(st, "msda_fwd_tile_kernel");
+    } else if (p.bin_off) {   // a backward will follow: count the sub-bin populations on the way
+        auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true, false, ROWB>;
         k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
-        prof_end(st);
-        MSDA_LAUNCHED("msda_fwd_tile_kernel");
-        return MSDA_OK;
+    } else {
+        auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false, false, ROWB>;
+        k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     }
-    auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, false>;
-    prof_begin(st, "msda_fwd_tile_kernel");
-    k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     prof_end(st);
-    MSDA_LAUNCHED("msda_fwd_tile_kernel");
+    MSDA_LAUNCHED(name);
     return MSDA_OK;
+}
+
+// The row pitch M*D*sizeof(T) is a compile-time constant for d_model = 256 on 8-lane rows (SOC's case:
+// 1024 B in fp32, 512 B in bf16); any other pitch takes the run-time variant.
+template <typename T, typename TA, int VEC, int G, int P>
+int launch_fwd_tile(const Params& p, cudaStream_t st) {
+    if constexpr (G == 8) {
+        constexpr int kPitch = 256 * (int)sizeof(T);
+        if (p.M * p.D * (int)sizeof(T) == kPitch) return launch_fwd_tile_rowb<T, TA, VEC, G, P, kPitch>(p, st);
+    }
+    return launch_fwd_tile_rowb<T, TA, VEC, G, P, 0>(p, st);
 }
 
 template <typename T, typename TA, typename CT>
@@ -235,14 +237,14 @@ int launch_fwd_generic(const Params& p, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // backward
-template <typename T, typename TA, int VEC, int G, int P>
-int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
+template <typename T, typename TA, int VEC, int G, int P, int ROWB>
+int launch_bwd_sample_tile_rowb(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;
     if constexpr (std::is_same<T, float>::value) {
         if (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) {
-            auto ka = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, false, true>;
+            auto ka = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, false, true, ROWB>;
             prof_begin(st, "msda_bwd_sample_tile_kernel<atomic>");
             ka<<<persistent_grid(ka, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
             prof_end(st);
@@ -250,12 +252,21 @@ int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
             return MSDA_OK;
         }
     }
-    auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false>;   // FILL: writes the index entries
+    auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false, ROWB>;   // FILL: writes the index entries
     prof_begin(st, "msda_bwd_sample_tile_kernel");
     k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
     prof_end(st);
     MSDA_LAUNCHED("msda_bwd_sample_tile_kernel");
     return MSDA_OK;
+}
+
+template <typename T, typename TA, int VEC, int G, int P>
+int launch_bwd_sample_tile(const Params& p, cudaStream_t st) {
+    if constexpr (G == 8) {
+        constexpr int kPitch = 256 * (int)sizeof(T);
+        if (p.M * p.D * (int)sizeof(T) == kPitch) return launch_bwd_sample_tile_rowb<T, TA, VEC, G, P, kPitch>(p, st);
+    }
+    return launch_bwd_sample_tile_rowb<T, TA, VEC, G, P, 0>(p, st);
 }
 
 template <typename T, typename TA, typename CT>
@@ -562,7 +573,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
     if (pl.tile && !(aligned16(value) && aligned16(output) && aligned16(sampling_loc) && aligned16(attn_weight)))
         pl.tile = false;
     if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;   // descriptor holds a 28-bit pixel index
-    if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 32)) pl.tile = false;  // 32-bit byte offsets
+    if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 31)) pl.tile = false;  // signed 32-bit byte offsets
 
     const bool aux32 = aux_dtype == MSDA_F32;
     const bool tile = pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16);

@@ -88,7 +88,7 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
 // part B (one integer atomic + one 16-byte store, overlapped with the gather).  ATOMIC:
 // bench-only A/B arm that scatters grad_value with 128-bit fp32 reductions like the reference
 // does with scalar ones.
-template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC>
+template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC, int ROWB = 0>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D;
         const char* fb = reinterpret_cast<const char*>(value) + frame_off * sizeof(T);
         asm volatile("" : "+l"(fb));         // keep the base in registers (ptxas would re-read it per load)
-        const uint32_t rowb = (uint32_t)row_elems * (uint32_t)sizeof(T);
+        const uint32_t rowb = ROWB ? (uint32_t)ROWB : (uint32_t)row_elems * (uint32_t)sizeof(T);
         const uint32_t lane_off = (uint32_t)(gl * VEC * sizeof(T));
         const uint4* drow = desc[buf] + grp * kDescStride;
         const int l0 = cur.c0 / P;
@@ -168,15 +168,17 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
 #pragma unroll
             for (int pp = 0; pp < PPC; ++pp) {
                 const uint4 d = drow[sbase + pp];
-                const uint32_t o0 = lp.base + (d.x & 0x0fffffffu) * rowb;
-                const uint32_t o2 = o0 + lp.wrow;
+                const int32_t o0 = lp.base + (int32_t)((d.x & 0x0fffffffu) * rowb);
+                const int32_t o2 = o0 + lp.wrow;
+                const char* p0 = fb + o0;                // top-left corner row (sign-extended offset)
+                const char* p2 = p0 + lp.wrow;           // the row below
                 float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o0), v0);
-                if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o0 + rowb)), v1);
-                if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o2), v2);
-                if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o2 + rowb)), v3);
+                if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0), v0);
+                if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0 + rowb), v1);
+                if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2), v2);
+                if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2 + rowb), v3);
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                     const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
                     const float w[4] = {ah * hw, ah * lw, al * hw, al * lw};
                     char* gvb = reinterpret_cast<char*>(p.grad_value) + frame_off * sizeof(T);
-                    const uint32_t oo[4] = {o0, o0 + rowb, o2, o2 + rowb};
+                    const int32_t oo[4] = {o0, o0 + (int32_t)rowb, o2, o2 + (int32_t)rowb};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((d.x >> (28 + k)) & 1u)

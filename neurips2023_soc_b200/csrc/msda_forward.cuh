@@ -35,7 +35,7 @@ namespace msda {
 // COUNT: also count the accepted samples per sub-bin for a backward that will follow.
 // FUSED: the softmax / sampling-location prologue of MSDeformAttn.forward runs in the staging
 // threads (TA is then the dtype of the raw offsets / logits; the results are fp32).
-template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool FUSED = false>
+template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool FUSED = false, int ROWB = 0>
 __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_kernel(const Params p, const int rounds) {
     constexpr int MODE = COUNT ? kIndexCount : kIndexNone;
     using TS = TileShape<G>;
@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
             const char* fb = reinterpret_cast<const char*>(value) +
                              ((size_t)tl.n * p.S * row_elems + tl.m * p.D) * sizeof(T);
             asm volatile("" : "+l"(fb));     // keep the base in registers (ptxas would re-read it per load)
-            const uint32_t rowb = (uint32_t)row_elems * (uint32_t)sizeof(T);
+            // bytes between horizontally adjacent pixels; known at compile time for the usual
+            // d_model (ROWB != 0), so that the second corner of a row pair is an immediate offset
+            const uint32_t rowb = ROWB ? (uint32_t)ROWB : (uint32_t)row_elems * (uint32_t)sizeof(T);
             const uint32_t lane_off = (uint32_t)(gl * VEC * sizeof(T));
             const uint4* drow = desc[buf] + grp * kDescStride;
             const int l0 = cur.c0 / P;
@@ -111,18 +113,18 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
 #pragma unroll
                 for (int pp = 0; pp < PPC; ++pp) {
                     const uint4 d = drow[sbase + pp];
-                    const uint32_t o0 = lp.base + (d.x & 0x0fffffffu) * rowb;
-                    const uint32_t o2 = o0 + lp.wrow;
+                    const char* p0 = fb + (lp.base + (int32_t)((d.x & 0x0fffffffu) * rowb));   // top-left corner row
+                    const char* p2 = p0 + lp.wrow;                                   // the row below
 #if !MSDA_FWD_STALE
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) v[pp][b][i] = 0.f;
 #endif
-                    if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o0), v[pp][0]);
-                    if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o0 + rowb)), v[pp][1]);
-                    if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + o2), v[pp][2]);
-                    if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(fb + (o2 + rowb)), v[pp][3]);
+                    if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0), v[pp][0]);
+                    if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0 + rowb), v[pp][1]);
+                    if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2), v[pp][2]);
+                    if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2 + rowb), v[pp][3]);
                     const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
                     const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
                     // a corner outside the map keeps whatever its registers held (a finite value of this

@@ -170,18 +170,19 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
     }
 }
 
-// Per-level constants of the gather.  Row addresses are 32-bit BYTE offsets from the base of
-// the tile's (frame, head) slice; arithmetic wraps modulo 2^32, which is harmless because
-// only offsets of corners inside the map (0 <= offset < S*M*D*sizeof(T) < 2^32) are used.
+// Per-level constants of the gather.  Row addresses are SIGNED 32-bit byte offsets from the base
+// of the tile's (frame, head) slice (S*M*D*sizeof(T) < 2^31 on this path): the top-left corner of a
+// sample may be the virtual pixel (row -1 / col -1) with a negative offset; it is never
+// dereferenced, but the other three corners are reached from it with 64-bit pointer adds.
 struct LevelPitch {
-    uint32_t base;   // byte offset of the virtual pixel (row -1, col -1) of the level, plus the lane's slice
-    uint32_t wrow;   // bytes between vertically adjacent pixels
+    int32_t base;    // byte offset of the virtual pixel (row -1, col -1) of the level, plus the lane's slice
+    int32_t wrow;    // bytes between vertically adjacent pixels
 };
 
 __device__ __forceinline__ LevelPitch level_pitch(const Level& L_, const uint32_t rowb, const uint32_t lane_off) {
     LevelPitch lp;
-    lp.base = (uint32_t)(L_.start - L_.W - 1) * rowb + lane_off;
-    lp.wrow = (uint32_t)L_.W * rowb;
+    lp.base = (L_.start - L_.W - 1) * (int32_t)rowb + (int32_t)lane_off;
+    lp.wrow = L_.W * (int32_t)rowb;
     return lp;
 }
 
