@@ -606,14 +606,14 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
     Entry<float> e;
     e.id = 0; e.lh = e.lw = e.a = 0.f;
     if (pos < end) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(ent + pos));
+        const uint4 t = ld_stream_b128(ent + pos);
         e.id = t.x; e.lh = __uint_as_float(t.y); e.lw = __uint_as_float(t.z); e.a = __uint_as_float(t.w);
     }
     return e;
 }
 
 #ifndef MSDA_WALK_MIN_BLOCKS
-#define MSDA_WALK_MIN_BLOCKS 5
+#define MSDA_WALK_MIN_BLOCKS 6
 #endif
 
 template <typename T, int VEC, int G>
@@ -623,7 +623,10 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
     constexpr int GW = 32 / G;                   // groups per warp
     constexpr int BR = (512 / D) < 2 ? 2 : (512 / D);   // bin rows per tile
     constexpr int TH = BR - 1, TW = kGTileW;
-    constexpr int STEP = VEC <= 4 ? 8 : 4;       // grad_output rows in flight per lane
+#ifndef MSDA_WALK_STEP
+#define MSDA_WALK_STEP 4
+#endif
+    constexpr int STEP = VEC <= 4 ? MSDA_WALK_STEP : 4;       // grad_output rows in flight per lane
     constexpr int NWARP = kGThreads / 32;
     // dense levels (many entries per bin) use small tiles -- one bin row per warp, 4 pixels wide -- so
     // that their long lists spread over many CTAs; the others use the full TH x TW tile

@@ -146,18 +146,43 @@ __device__ __forceinline__ void store_row(T* p, const float (&v)[VEC]) {
     *reinterpret_cast<R*>(p) = t;
 }
 
+// Streaming loads (data read exactly once: locations, weights, index entries): read-only path,
+// no L1 allocation, so that L1 keeps the value / grad_output rows the gathers re-use.
+__device__ __forceinline__ uint32_t ld_stream_b32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_b64(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_stream_b128(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) { return __uint_as_float(ld_stream_b32(p)); }
+__device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+}
+__device__ __forceinline__ float ld_stream(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldg(p); }
+
 // sampling location (x, y) and attention weight loads in the aux dtype
 template <typename CT> struct XY { CT x, y; };
 __device__ __forceinline__ XY<float> load_xy(const float* p) {
-    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
-    return {t.x, t.y};
+    const uint2 t = ld_stream_b64(p);
+    return {__uint_as_float(t.x), __uint_as_float(t.y)};
 }
 __device__ __forceinline__ XY<float> load_xy(const __nv_bfloat16* p) {
-    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const uint32_t t = ld_stream_b32(p);
     return {__uint_as_float(t << 16), __uint_as_float(t & 0xffff0000u)};
 }
 __device__ __forceinline__ XY<float> load_xy(const __half* p) {
-    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const uint32_t t = ld_stream_b32(p);
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
     return {f.x, f.y};
 }

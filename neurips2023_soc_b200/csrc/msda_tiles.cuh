@@ -71,7 +71,7 @@ __device__ __forceinline__ void stage_load(Staged<TileShape<G>::DPT>& st, const 
             const size_t si = (((size_t)tl.n * p.Lq + q) * p.M + tl.m) * p.LP + sg;
             const XY<float> xy = load_xy(loc + 2 * si);
             st.x[k] = xy.x; st.y[k] = xy.y;
-            st.a[k] = Elem<TA>::to_f(__ldg(attn + si));
+            st.a[k] = (float)ld_stream(attn + si);
             if constexpr (FUSED) {
                 const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) +
                                        ((size_t)tl.n * p.Lq + q) * p.L + min(sg / P, p.L - 1));
