@@ -75,6 +75,19 @@ class MSDeformAttn(nn.Module):
             nn.init.xavier_uniform_(self.output_proj.weight)
             self.output_proj.bias.zero_()
 
+    def _check_geometry(self, shapes: torch.Tensor, S: int) -> None:
+        """The reference asserts ``sum(H_l * W_l) == S`` on every call (ms_deform_attn.py:93), which is a
+        device-to-host synchronisation per layer when the shapes live on the GPU (they do:
+        /root/reference/models/deformable_transformer.py:164).  Same check, but once per distinct shapes
+        tensor, and never while a CUDA graph is being captured."""
+        key = (shapes.data_ptr(), shapes._version, tuple(shapes.shape), S)
+        if key == getattr(self, "_geometry_ok", None):
+            return
+        if shapes.is_cuda and torch.cuda.is_current_stream_capturing():
+            return
+        assert int((shapes[:, 0] * shapes[:, 1]).sum()) == S
+        self._geometry_ok = key
+
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
                 input_padding_mask=None):
         """query (N, Lq, C); reference_points (N, Lq, L, 2|4) in [0, 1]; input_flatten (N, S, C);
@@ -84,7 +97,7 @@ class MSDeformAttn(nn.Module):
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         M, L, P = self.n_heads, self.n_levels, self.n_points
-        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == S
+        self._check_geometry(input_spatial_shapes, S)
 
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
