@@ -102,7 +102,8 @@ int msda_forward_ex(const void *value, const int64_t *spatial_shapes, const int6
  * sub-bin of the inverse index the backward's grad_value gather uses; it leaves the exclusive
  * scan of those counts in `index` (msda_index_bytes bytes of device memory, 16-byte aligned,
  * owned by the caller, to be kept unchanged until the backward).  msda_backward_indexed then
- * skips its own counting pass.  With index == NULL both calls behave like the plain ones.
+ * skips its own counting pass and CONSUMES the buffer (it advances the offsets in place; pass a
+ * copy to run a second backward).  With index == NULL both calls behave like the plain ones.
  * The reference's autograd function has no such state (it saves inputs only,
  * ms_deform_attn_func.py:27); the index is a pure function of the saved inputs. */
 size_t msda_index_bytes(int N, int S, int M, int D, int L, int Lq, int P);
@@ -116,7 +117,7 @@ int msda_forward_indexed(const void *value, const int64_t *spatial_shapes, const
 int msda_backward_indexed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                           const void *sampling_loc, const void *attn_weight, const void *grad_output,
                           void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
-                          void *workspace, size_t workspace_bytes, const void *index, size_t index_bytes,
+                          void *workspace, size_t workspace_bytes, void *index, size_t index_bytes,
                           int N, int S, int M, int D, int L, int Lq, int P,
                           int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
 

@@ -423,7 +423,7 @@ size_t index_bytes(int N, int S, int M, int L, int Lq, int P) {
 
 // workspace layout (bytes, every region 256-byte aligned)
 struct WsLayout {
-    size_t bin_off, cursor, counts, big, entries, total;
+    size_t bin_off, counts, big, entries, total;
     int sb_max, big_cap;
 };
 
@@ -437,8 +437,7 @@ WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
     const size_t entry = vdt == MSDA_F64 ? sizeof(Entry<double>) : sizeof(Entry<float>);
     const size_t table = index_bytes(N, S, M, L, Lq, P);
     w.bin_off = 0;
-    w.cursor = align256(table);
-    w.counts = align256(w.cursor + table);
+    w.counts = align256(table);
     w.big = align256(w.counts + 4 * sizeof(uint32_t));
     w.entries = align256(w.big + 2 * (size_t)w.big_cap * sizeof(uint32_t));
     w.total = align256(w.entries + samples * entry);
@@ -446,7 +445,7 @@ WsLayout ws_layout(int N, int S, int M, int L, int Lq, int P, int vdt) {
 }
 
 template <typename T, typename TA, typename CT>
-int backward_typed(Params& p, const Plan& pl, int vdt, const void* index, size_t table_bytes, cudaStream_t st) {
+int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table_bytes, cudaStream_t st) {
     int rc;
     bool tile = pl.tile;
     if constexpr (std::is_same<T, double>::value || std::is_same<T, __half>::value) tile = false;
@@ -454,8 +453,8 @@ int backward_typed(Params& p, const Plan& pl, int vdt, const void* index, size_t
     if (!atomic_arm) {
         // sub-bin offsets: handed over by the forward, or counted and scanned here
         if (index) {
-            // read-only from here on: the sort and the walker only look offsets up
-            p.bin_off = const_cast<uint32_t*>(static_cast<const uint32_t*>(index));
+            // consumed: the fill advances the start offsets in place into end offsets
+            p.bin_off = static_cast<uint32_t*>(index);
         } else {
             prof_begin(st, "memset(bin table)");
             MSDA_CUDA(cudaMemsetAsync(p.bin_off, 0, table_bytes, st));
@@ -463,11 +462,8 @@ int backward_typed(Params& p, const Plan& pl, int vdt, const void* index, size_t
             ++g_launches;
             if ((rc = launch_count_scan<TA, CT>(p, true, st))) return rc;
         }
-        prof_begin(st, "memcpy(cursor)");
-        MSDA_CUDA(cudaMemcpyAsync(p.cursor, p.bin_off, table_bytes, cudaMemcpyDeviceToDevice, st));
         MSDA_CUDA(cudaMemsetAsync(p.counts, 0, 4 * sizeof(uint32_t), st));
-        prof_end(st);
-        g_launches += 2;
+        ++g_launches;
     }
     if (tile) {
         if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
@@ -653,7 +649,7 @@ size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, 
 int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                           const void* sampling_loc, const void* attn_weight, const void* grad_output,
                           void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
-                          size_t workspace_bytes, const void* index, size_t index_size, int N, int S, int M, int D,
+                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
                           int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
                           unsigned flags) {
     g_launches = 0;
@@ -693,7 +689,6 @@ int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, cons
     if (need_ws) {
         char* base = static_cast<char*>(workspace);
         p.bin_off = reinterpret_cast<uint32_t*>(base + w.bin_off);
-        p.cursor = reinterpret_cast<uint32_t*>(base + w.cursor);
         p.counts = reinterpret_cast<uint32_t*>(base + w.counts);
         p.big_bins = reinterpret_cast<uint32_t*>(base + w.big);
         p.entries = base + w.entries;

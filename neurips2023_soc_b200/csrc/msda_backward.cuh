@@ -361,19 +361,23 @@ __global__ void __launch_bounds__(kThreads) msda_bin_count_kernel(const Params p
         const Sample<CT> s = locate(xy.x, xy.y, L_.H, L_.W);
         if (s.ok) {
             const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
-            atomicAdd(p.bin_off + (size_t)(r.n * p.M + r.m) * (p.sb_max + 1) + bin, 1u);
+            atomicAdd(p.bin_off + (size_t)(r.n * p.M + r.m) * (p.sb_max + 1) + bin + 1, 1u);
         }
     }
 }
 
-// One CTA per (frame, head): in-place exclusive scan of the sub-bin counts.
+// One CTA per (frame, head): in-place exclusive scan of the sub-bin counts.  The count of sub-bin b
+// sits in slot b+1 of the table row (slot 0 stays 0), so that after the scan slot b+1 holds the
+// START of sub-bin b, and after the fill has advanced it by the sub-bin's population it holds its
+// END, which is the start of sub-bin b+1: from then on (row[b], row[b+1]) is the range of sub-bin b
+// and no second copy of the table is needed.
 __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     __shared__ uint32_t warp_tot[32];
     load_levels(p, lv, &s_sb, &s_sq);
     const int nm = blockIdx.x;
-    uint32_t* data = p.bin_off + (size_t)nm * (p.sb_max + 1);
+    uint32_t* data = p.bin_off + (size_t)nm * (p.sb_max + 1) + 1;
     const int SB = s_sb;
     const int ipt = (SB + blockDim.x - 1) / blockDim.x;
     const int beg = min(SB, (int)threadIdx.x * ipt), end = min(SB, beg + ipt);
@@ -406,7 +410,6 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
         data[i] = run;
         run += c;
     }
-    if (threadIdx.x == blockDim.x - 1) data[SB] = run;  // last thread's running total == grand total
 }
 
 template <typename TA, typename CT>
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
         if (!s.ok) continue;
         const int bin = sub_bin(L_, s.h_lo, s.w_lo, r.q);
         const size_t nm = (size_t)r.n * p.M + r.m;
-        const uint32_t slot = atomicAdd(p.cursor + nm * (p.sb_max + 1) + bin, 1u);
+        const uint32_t slot = atomicAdd(p.bin_off + nm * (p.sb_max + 1) + bin + 1, 1u);
         Entry<CT> e;
         e.id = ((uint32_t)r.q << p.id_shift) | (uint32_t)r.sg;
         e.lh = s.lh; e.lw = s.lw;

@@ -45,8 +45,8 @@ struct Params {
     void* grad_loc;
     void* grad_attn;
     // backward workspace (see msda_backward.cuh)
-    uint32_t* bin_off;       // [N*M][sb_max + 1]  sub-bin counts, then their exclusive scan
-    uint32_t* cursor;        // [N*M][sb_max + 1]  copy of the offsets that the fill advances
+    uint32_t* bin_off;       // [N*M][sb_max + 1]  row[0] = 0, row[b+1]: count of sub-bin b -> its start offset
+                             //                    (scan) -> its end offset (fill); readers use row[b], row[b+1]
     void* entries;           // [N*M][Lq*L*P]      per-bin contribution lists
     uint32_t* counts;        // [0] entries in big_bins (right behind bin_off so one memset clears both)
     uint32_t* big_bins;      // (nm, sub-bin) pairs of sub-bins with > 32 entries

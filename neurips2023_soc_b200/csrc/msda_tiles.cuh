@@ -122,8 +122,9 @@ __device__ __forceinline__ void fused_prologue(Staged<TileShape<G>::DPT>& st, co
 //   kIndexNone   nothing (plain forward)
 //   kIndexCount  count the accepted samples of every sub-bin (forward that will be followed by a
 //                backward: the scan of these counts is handed to it)
-//   kIndexFill   take a slot from the sub-bin's cursor (initialised to its exclusive offset)
-//                and write the sample's 16-byte entry there (backward)
+//   kIndexFill   take a slot by advancing the sub-bin's offset in the table (which turns the row of
+//                start offsets into the row of end offsets = the next sub-bin's start) and write
+//                the sample's 16-byte entry there (backward)
 // Only integer atomics are involved; they decide where an entry sits before sorting, never a
 // floating-point result.
 constexpr int kIndexNone = 0, kIndexCount = 1, kIndexFill = 2;
@@ -153,11 +154,12 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
                 d.w = __float_as_uint(st.a[k]);
                 if constexpr (MODE != kIndexNone) {
                     const size_t nm = (size_t)tl.n * p.M + tl.m;
-                    const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]);
+                    // slot b+1 of the table row belongs to sub-bin b (see msda_bin_scan_kernel)
+                    const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]) + 1;
                     if constexpr (MODE == kIndexCount) {
                         atomicAdd(p.bin_off + b, 1u);
                     } else {
-                        const uint32_t slot = atomicAdd(p.cursor + b, 1u);
+                        const uint32_t slot = atomicAdd(p.bin_off + b, 1u);
                         uint4 e;
                         e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;
                         e.y = d.y; e.z = d.z; e.w = d.w;

@@ -71,7 +71,7 @@ def _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                            im2col_step: int, flags: int | None = None, want_index: bool = False):
     """``want_index=True`` (not part of the reference signature) also returns the index the matching
-    backward can reuse: ``(output, index)`` -- see msda_forward_indexed in include/msda_b200.h."""
+    backward can use -- and uses up: ``(output, index)``, see msda_forward_indexed in include/msda_b200.h."""
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
     dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
