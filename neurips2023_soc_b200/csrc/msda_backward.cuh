@@ -248,8 +248,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
                     const size_t si = qm_mine * p.LP + sgo;
                     gattn[si] = Elem<TA>::from_f(ga);
-                    gloc[2 * si] = Elem<TA>::from_f((float)L_.W * a * gx);
-                    gloc[2 * si + 1] = Elem<TA>::from_f((float)L_.H * a * gy);
+                    store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
                 }
             }
         }
@@ -446,12 +445,12 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
 // about six entries) and is written back to `first slot + rank`.  All lanes do the same amount
 // of work whatever the sub-bin sizes are.  Sub-bins with more than kRankMax entries go to the
 // big list instead (msda_bin_sort_big_kernel: bitonic network, one CTA per sub-bin).
-constexpr int kRankSpan = 256;   // sub-bins staged per step (at most)
+constexpr int kRankSpan = 128;   // sub-bins staged per step (at most)
 constexpr int kRankMax = 512;    // largest sub-bin ranked by counting
 
 template <typename CT>
 __global__ void __launch_bounds__(kThreads) msda_bin_rank_sort_kernel(const Params p) {
-    constexpr int CAP = 32768 / (int)sizeof(Entry<CT>);     // entries staged per step
+    constexpr int CAP = 16384 / (int)sizeof(Entry<CT>);     // entries staged per step
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     __shared__ Entry<CT> buf[CAP];
@@ -477,17 +476,20 @@ __global__ void __launch_bounds__(kThreads) msda_bin_rank_sort_kernel(const Para
             const int n = min(kRankSpan, b_end - b);
             for (int i = tid; i <= n; i += kThreads) soff[i] = off[b + i];
             __syncthreads();
-            if (tid == 0) {
-                // as many whole sub-bins as fit the staging buffer (at least one)
-                int lo = 1, hi = n;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (soff[mid] - soff[0] <= (uint32_t)CAP) lo = mid; else hi = mid - 1;
+            int take = n;                       // usually the whole span fits the staging buffer
+            if (soff[n] - soff[0] > (uint32_t)CAP) {            // uniform: everybody reads the same two words
+                if (tid == 0) {
+                    // as many whole sub-bins as fit (at least one)
+                    int lo = 1, hi = n;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (soff[mid] - soff[0] <= (uint32_t)CAP) lo = mid; else hi = mid - 1;
+                    }
+                    s_take = lo;
                 }
-                s_take = lo;
+                __syncthreads();
+                take = s_take;
             }
-            __syncthreads();
-            const int take = s_take;
             const uint32_t base = soff[0];
             const uint32_t cnt_e = soff[take] - base;
             if (cnt_e <= (uint32_t)CAP) {

@@ -191,6 +191,15 @@ __device__ __forceinline__ XY<double> load_xy(const double* p) {
     return {t.x, t.y};
 }
 
+// (x, y) pair store in the aux dtype: one 64-bit (32-bit for 16-bit types) store
+__device__ __forceinline__ void store_xy(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
+__device__ __forceinline__ void store_xy(__nv_bfloat16* p, float x, float y) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
+}
+__device__ __forceinline__ void store_xy(__half* p, float x, float y) {
+    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(x, y);
+}
+
 // ---------------------------------------------------------------------------------------
 // geometry of one sample
 template <typename CT> struct Sample {
