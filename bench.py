@@ -228,7 +228,7 @@ def run_ours(args):
         "msda_fwd_tile_kernel": fwd_bytes,
         "msda_bwd_sample_tile_kernel": vb * N * S * C + vb * N * Lq * C + ab * samples * 3 + ab * samples * 3 + 16 * samples,
         "msda_grad_value_walk_kernel": vb * N * Lq * C + 16 * samples + vb * N * S * C,
-        "msda_bin_sort_small_kernel": 2 * 16 * samples,
+        "msda_bin_rank_sort_kernel": 2 * 16 * samples,
     }
     peak, peak_src = peaks()
     dom_bytes = alg.get(dominant, bwd_bytes)
