@@ -172,20 +172,36 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 const int32_t o2 = o0 + lp.wrow;
                 const char* p0 = fb + o0;                // top-left corner row (sign-extended offset)
                 const char* p2 = p0 + lp.wrow;           // the row below
+                using R = typename Raw<sizeof(T) * VEC>::type;
+                const R r0 = load_raw_if<T, VEC>(d.x & (1u << 28), reinterpret_cast<const T*>(p0));
+                const R r1 = load_raw_if<T, VEC>(d.x & (2u << 28), reinterpret_cast<const T*>(p0 + rowb));
+                const R r2 = load_raw_if<T, VEC>(d.x & (4u << 28), reinterpret_cast<const T*>(p2));
+                const R r3 = load_raw_if<T, VEC>(d.x & (8u << 28), reinterpret_cast<const T*>(p2 + rowb));
                 float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) v0[i] = v1[i] = v2[i] = v3[i] = 0.f;
-                if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0), v0);
-                if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0 + rowb), v1);
-                if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2), v2);
-                if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2 + rowb), v3);
+                unpack_row<T, VEC>(r0, v0);
+                unpack_row<T, VEC>(r1, v1);
+                unpack_row<T, VEC>(r2, v2);
+                unpack_row<T, VEC>(r3, v3);
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                if constexpr (use_packed_fma<T, 1>()) {
+                    // even / odd channel partial sums on packed fp32x2 FMAs, added at the end
+                    float o0_ = 0.f, o1_ = 0.f, o2_ = 0.f, o3_ = 0.f;
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    d0 = fmaf(g[i], v0[i], d0);
-                    d1 = fmaf(g[i], v1[i], d1);
-                    d2 = fmaf(g[i], v2[i], d2);
-                    d3 = fmaf(g[i], v3[i], d3);
+                    for (int i = 0; i < VEC; i += 2) {
+                        fma2v(d0, o0_, g[i], g[i + 1], v0[i], v0[i + 1]);
+                        fma2v(d1, o1_, g[i], g[i + 1], v1[i], v1[i + 1]);
+                        fma2v(d2, o2_, g[i], g[i + 1], v2[i], v2[i + 1]);
+                        fma2v(d3, o3_, g[i], g[i + 1], v3[i], v3[i + 1]);
+                    }
+                    d0 += o0_; d1 += o1_; d2 += o2_; d3 += o3_;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        d0 = fmaf(g[i], v0[i], d0);
+                        d1 = fmaf(g[i], v1[i], d1);
+                        d2 = fmaf(g[i], v2[i], d2);
+                        d3 = fmaf(g[i], v3[i], d3);
+                    }
                 }
                 part[4 * pp + 0] = d0; part[4 * pp + 1] = d1;
                 part[4 * pp + 2] = d2; part[4 * pp + 3] = d3;
@@ -745,27 +761,29 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
 #pragma unroll
                     for (int c0 = 0; c0 < G; c0 += STEP) {
                         if (c0 >= nbat) break;
-                        float gv[STEP][VEC];
+                        using R = typename Raw<sizeof(T) * VEC>::type;
+                        R raw[STEP];
 #pragma unroll
                         for (int e = 0; e < STEP; ++e) {
                             const uint32_t q = __shfl_sync(gmask, myq, c0 + e, G);
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) gv[e][i] = 0.f;
-                            if (c0 + e < nbat) load_row<T, VEC>(gbase + (size_t)q * qstride, gv[e]);
+                            // entries past nbat carry zero weights and zero rows
+                            raw[e] = load_raw_if<T, VEC>(c0 + e < nbat, gbase + (size_t)q * qstride);
                         }
 #pragma unroll
                         for (int e = 0; e < STEP; ++e) {
-                            // entries past nbat carry zero weights and zero rows
                             const float w0 = __shfl_sync(gmask, myw[0], c0 + e, G);
                             const float w1 = __shfl_sync(gmask, myw[1], c0 + e, G);
                             const float w2 = __shfl_sync(gmask, myw[2], c0 + e, G);
                             const float w3 = __shfl_sync(gmask, myw[3], c0 + e, G);
+                            float gv[VEC];
+                            unpack_row<T, VEC>(raw[e], gv);
+                            constexpr bool PK = use_packed_fma<T, 2>();
 #pragma unroll
-                            for (int i = 0; i < VEC; ++i) {
-                                acc.g1[i] = fmaf(w0, gv[e][i], acc.g1[i]);
-                                acc.g2[i] = fmaf(w1, gv[e][i], acc.g2[i]);
-                                acc.g3[i] = fmaf(w2, gv[e][i], acc.g3[i]);
-                                acc.g4[i] = fmaf(w3, gv[e][i], acc.g4[i]);
+                            for (int i = 0; i < VEC; i += 2) {
+                                axpy2<PK>(acc.g1[i], acc.g1[i + 1], w0, gv[i], gv[i + 1]);
+                                axpy2<PK>(acc.g2[i], acc.g2[i + 1], w1, gv[i], gv[i + 1]);
+                                axpy2<PK>(acc.g3[i], acc.g3[i + 1], w2, gv[i], gv[i + 1]);
+                                axpy2<PK>(acc.g4[i], acc.g4[i + 1], w3, gv[i], gv[i + 1]);
                             }
                         }
                     }

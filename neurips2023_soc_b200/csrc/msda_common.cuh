@@ -122,6 +122,85 @@ __device__ __forceinline__ void load_row(const T* p, float (&v)[VEC]) {
     }
 }
 
+// The same in two steps for the gathers: a predicated load into zeroed RAW registers, then an
+// unconditional unpack -- cheaper than predicating the unpack of every channel.
+template <typename T, int VEC>
+__device__ __forceinline__ typename Raw<sizeof(T) * VEC>::type load_raw_if(const bool ok, const T* p) {
+    using R = typename Raw<sizeof(T) * VEC>::type;
+    R t;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(R) / 4); ++i) w[i] = 0u;
+    if (ok) t = __ldg(reinterpret_cast<const R*>(p));
+    return t;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void unpack_row(const typename Raw<sizeof(T) * VEC>::type& t, float (&v)[VEC]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&t);
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = __uint_as_float(w[i]);
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+}
+
+// (a0, a1) += w * (v0, v1) as ONE packed fp32x2 FMA (FFMA2 on sm_100): each half is an IEEE fma, so
+// the result is bit-identical to two scalar fmaf calls at half the issue slots.
+__device__ __forceinline__ void fma2(float& a0, float& a1, const float w, const float v0, const float v1) {
+    uint64_t acc, vv, ww;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(ww), "l"(vv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+}
+
+// Which kernels use the packed FMA (measured on B200: it pays for 16-bit rows, whose unpack leaves
+// the channel pairs in adjacent registers anyway; for fp32 rows it is neutral to slower).
+// bit 0: forward gather, bit 1: sample gradients, bit 2: grad_value walk
+#ifndef MSDA_PACK_F32
+#define MSDA_PACK_F32 0
+#endif
+#ifndef MSDA_PACK_16
+#define MSDA_PACK_16 7
+#endif
+template <typename T, int BIT>
+__host__ __device__ constexpr bool use_packed_fma() { return (((sizeof(T) == 2) ? MSDA_PACK_16 : MSDA_PACK_F32) >> BIT) & 1; }
+
+// (a0, a1) += w * (v0, v1): packed or two scalar FMAs, same bits either way
+template <bool PACKED>
+__device__ __forceinline__ void axpy2(float& a0, float& a1, const float w, const float v0, const float v1) {
+    if constexpr (PACKED) {
+        fma2(a0, a1, w, v0, v1);
+    } else {
+        a0 = fmaf(w, v0, a0);
+        a1 = fmaf(w, v1, a1);
+    }
+}
+
+// (a0, a1) += (u0, u1) * (v0, v1), packed
+__device__ __forceinline__ void fma2v(float& a0, float& a1, const float u0, const float u1, const float v0,
+                                      const float v1) {
+    uint64_t acc, vv, uu;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(uu) : "f"(u0), "f"(u1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(uu), "l"(vv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+}
+
 template <typename T, int VEC>
 __device__ __forceinline__ void store_row(T* p, const float (&v)[VEC]) {
     using R = typename Raw<sizeof(T) * VEC>::type;

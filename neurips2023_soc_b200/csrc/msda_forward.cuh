@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
 
     int buf = 0;
     float acc[VEC];
-    float v[PPC][4][VEC];      // corner rows in flight; zeroed once per output row (see the weights below)
     while (true) {
         const Work nxt = next_work(cur, rounds, p.LP);
         const bool has_next = nxt.t < total_tiles;
@@ -86,12 +85,6 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
         if (cur.c0 == 0) {
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-#pragma unroll
-            for (int a = 0; a < PPC; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) v[a][b][i] = 0.f;
         }
         if (q_mine >= 0) {
             // all addresses of a tile are 32-bit byte offsets from one CTA-uniform base
@@ -115,34 +108,28 @@ __global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_k
                     const uint4 d = drow[sbase + pp];
                     const char* p0 = fb + (lp.base + (int32_t)((d.x & 0x0fffffffu) * rowb));   // top-left corner row
                     const char* p2 = p0 + lp.wrow;                                   // the row below
-#if !MSDA_FWD_STALE
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) v[pp][b][i] = 0.f;
-#endif
-                    if (d.x & (1u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0), v[pp][0]);
-                    if (d.x & (2u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p0 + rowb), v[pp][1]);
-                    if (d.x & (4u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2), v[pp][2]);
-                    if (d.x & (8u << 28)) load_row<T, VEC>(reinterpret_cast<const T*>(p2 + rowb), v[pp][3]);
+                    using R = typename Raw<sizeof(T) * VEC>::type;
+                    // predicated loads into zeroed raw registers: a corner outside the map contributes
+                    // exactly 0 whatever its weight
+                    const R r0 = load_raw_if<T, VEC>(d.x & (1u << 28), reinterpret_cast<const T*>(p0));
+                    const R r1 = load_raw_if<T, VEC>(d.x & (2u << 28), reinterpret_cast<const T*>(p0 + rowb));
+                    const R r2 = load_raw_if<T, VEC>(d.x & (4u << 28), reinterpret_cast<const T*>(p2));
+                    const R r3 = load_raw_if<T, VEC>(d.x & (8u << 28), reinterpret_cast<const T*>(p2 + rowb));
                     const float lh = __uint_as_float(d.y), lw = __uint_as_float(d.z), a = __uint_as_float(d.w);
                     const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
-                    // a corner outside the map keeps whatever its registers held (a finite value of this
-                    // row, or the row is NaN already) and gets an exactly zero weight
-#if MSDA_FWD_STALE
-                    const float w0 = (d.x & (1u << 28)) ? ah * hw : 0.f;
-                    const float w1 = (d.x & (2u << 28)) ? ah * lw : 0.f;
-                    const float w2 = (d.x & (4u << 28)) ? al * hw : 0.f;
-                    const float w3 = (d.x & (8u << 28)) ? al * lw : 0.f;
-#else
                     const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
-#endif
+                    float v0[VEC], v1[VEC], v2[VEC], v3[VEC];
+                    unpack_row<T, VEC>(r0, v0);
+                    unpack_row<T, VEC>(r1, v1);
+                    unpack_row<T, VEC>(r2, v2);
+                    unpack_row<T, VEC>(r3, v3);
+                    constexpr bool PK = use_packed_fma<T, 0>();
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) {
-                        acc[i] = fmaf(w0, v[pp][0][i], acc[i]);
-                        acc[i] = fmaf(w1, v[pp][1][i], acc[i]);
-                        acc[i] = fmaf(w2, v[pp][2][i], acc[i]);
-                        acc[i] = fmaf(w3, v[pp][3][i], acc[i]);
+                    for (int i = 0; i < VEC; i += 2) {
+                        axpy2<PK>(acc[i], acc[i + 1], w0, v0[i], v0[i + 1]);
+                        axpy2<PK>(acc[i], acc[i + 1], w1, v1[i], v1[i + 1]);
+                        axpy2<PK>(acc[i], acc[i + 1], w2, v2[i], v2[i + 1]);
+                        axpy2<PK>(acc[i], acc[i + 1], w3, v3[i], v3[i + 1]);
                     }
                 }
             }
