@@ -125,7 +125,10 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
     __syncthreads();
 
     int buf = 0;
-    float g[VEC];
+    using R = typename Raw<sizeof(T) * VEC>::type;
+    constexpr bool BF16_DOT = std::is_same<T, __nv_bfloat16>::value && MSDA_BF16_MIXED_FMA;
+    R graw = {};                                     // this row's grad_output slice: as loaded (BF16_DOT) ...
+    float g[VEC];                                    // ... or unpacked
     while (true) {
         const Work nxt = next_work(cur, rounds, p.LP);
         const bool has_next = nxt.t < total_tiles;
@@ -138,9 +141,13 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);
         const size_t qm_mine = ((size_t)tl.n * p.Lq + (q_mine < 0 ? 0 : q_mine)) * p.M + tl.m;
         if (cur.c0 == 0) {
+            if constexpr (BF16_DOT) {
+                graw = load_raw_if<T, VEC>(q_mine >= 0, gout + qm_mine * p.D + gl * VEC);
+            } else {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) g[i] = 0.f;
-            if (q_mine >= 0) load_row<T, VEC>(gout + qm_mine * p.D + gl * VEC, g);
+                for (int i = 0; i < VEC; ++i) g[i] = 0.f;
+                if (q_mine >= 0) load_row<T, VEC>(gout + qm_mine * p.D + gl * VEC, g);
+            }
         }
         const size_t frame_off = (size_t)tl.n * p.S * row_elems + tl.m * p.D;
         const char* fb = reinterpret_cast<const char*>(value) + frame_off * sizeof(T);
@@ -172,7 +179,6 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 const int32_t o2 = o0 + lp.wrow;
                 const char* p0 = fb + o0;                // top-left corner row (sign-extended offset)
                 const char* p2 = p0 + lp.wrow;           // the row below
-                using R = typename Raw<sizeof(T) * VEC>::type;
                 const R r0 = load_raw_if<T, VEC>(d.x & (1u << 28), reinterpret_cast<const T*>(p0));
                 const R r1 = load_raw_if<T, VEC>(d.x & (2u << 28), reinterpret_cast<const T*>(p0 + rowb));
                 const R r2 = load_raw_if<T, VEC>(d.x & (4u << 28), reinterpret_cast<const T*>(p2));
@@ -183,7 +189,21 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 unpack_row<T, VEC>(r2, v2);
                 unpack_row<T, VEC>(r3, v3);
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-                if constexpr (use_packed_fma<T, 1>()) {
+                if constexpr (BF16_DOT) {
+                    // bf16 x bf16 -> fp32 FMAs straight from the packed registers, channel by channel
+                    const uint32_t* gw = reinterpret_cast<const uint32_t*>(&graw);
+                    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(&r0);
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(&r1);
+                    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(&r2);
+                    const uint32_t* w3 = reinterpret_cast<const uint32_t*>(&r3);
+#pragma unroll
+                    for (int i = 0; i < VEC / 2; ++i) {
+                        dot2_bf16(d0, gw[i], w0[i]);
+                        dot2_bf16(d1, gw[i], w1[i]);
+                        dot2_bf16(d2, gw[i], w2[i]);
+                        dot2_bf16(d3, gw[i], w3[i]);
+                    }
+                } else if constexpr (use_packed_fma<T, 1>()) {
                     // even / odd channel partial sums on packed fp32x2 FMAs, added at the end
                     float o0_ = 0.f, o1_ = 0.f, o2_ = 0.f, o3_ = 0.f;
 #pragma unroll

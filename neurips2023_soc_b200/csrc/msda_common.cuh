@@ -167,6 +167,18 @@ __device__ __forceinline__ void fma2(float& a0, float& a1, const float w, const 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
 }
 
+// acc += a.lo * b.lo, then acc += a.hi * b.hi for two packed bf16 pairs, on the mixed-precision FMA of
+// sm_100 (FHFMA.BF16 reads either half of a 32-bit register: no unpack).  A bf16 x bf16 product is exact
+// in fp32, so each step equals fmaf(float(a), float(b), acc) bit for bit.
+__device__ __forceinline__ void dot2_bf16(float& acc, const uint32_t a, const uint32_t b) {
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t"
+        "mov.b32 {al, ah}, %1;\n\t"
+        "mov.b32 {bl, bh}, %2;\n\t"
+        "fma.rn.f32.bf16 %0, al, bl, %0;\n\t"
+        "fma.rn.f32.bf16 %0, ah, bh, %0;\n\t}"
+        : "+f"(acc) : "r"(a), "r"(b));
+}
+
 // Which kernels use the packed FMA (measured on B200: it pays for 16-bit rows, whose unpack leaves
 // the channel pairs in adjacent registers anyway; for fp32 rows it is neutral to slower).
 // bit 0: forward gather, bit 1: sample gradients, bit 2: grad_value walk
@@ -175,6 +187,10 @@ __device__ __forceinline__ void fma2(float& a0, float& a1, const float w, const 
 #endif
 #ifndef MSDA_PACK_16
 #define MSDA_PACK_16 7
+#endif
+// sample gradients with bf16 rows: dot products on FHFMA.BF16 instead of unpack + fp32 FMAs
+#ifndef MSDA_BF16_MIXED_FMA
+#define MSDA_BF16_MIXED_FMA 1
 #endif
 template <typename T, int BIT>
 __host__ __device__ constexpr bool use_packed_fma() { return (((sizeof(T) == 2) ? MSDA_PACK_16 : MSDA_PACK_F32) >> BIT) & 1; }
