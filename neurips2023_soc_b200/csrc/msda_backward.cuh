@@ -669,9 +669,16 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
 #endif
     constexpr int STEP = VEC <= 4 ? MSDA_WALK_STEP : 4;       // grad_output rows in flight per lane
     constexpr int NWARP = kGThreads / 32;
-    // dense levels (many entries per bin) use small tiles -- one bin row per warp, 4 pixels wide -- so
-    // that their long lists spread over many CTAs; the others use the full TH x TW tile
-    constexpr int TH_D = NWARP - 1 < TH ? NWARP - 1 : TH, TW_D = 4;
+    // dense levels (many entries per bin): a warp walks a bin row and its groups share every bin; their
+    // tiles are a little smaller (12 x 8; measured 3 x 4 .. 12 x 8: the halo of re-walked bins costs more
+    // than the coarser load balance), the other levels use the full TH x TW tile
+#ifndef MSDA_WALK_THD
+#define MSDA_WALK_THD 12
+#endif
+#ifndef MSDA_WALK_TWD
+#define MSDA_WALK_TWD 8
+#endif
+    constexpr int TH_D = (MSDA_WALK_THD) < TH ? (MSDA_WALK_THD) : TH, TW_D = MSDA_WALK_TWD;
 
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
