@@ -1,0 +1,161 @@
+"""The op for batches that live in HOST memory: forward + backward streamed over the frames.
+
+The reference keeps its frames on the device for the whole step
+(/root/reference/models/deformable_transformer.py:191-205), so it has no host entry point; a caller
+that holds the tensors of a step in host memory (a data-loader thread, a CPU stage of a pipeline, a
+benchmark timing the op end to end) pays the PCIe transfers around the kernels.  Frames are
+independent in both passes (/root/reference/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:263-269),
+so the transfers can hide each other and the kernels: the batch is cut into chunks of a few frames
+and three streams run a software pipeline
+
+    copy-in stream   H2D(chunk i+1)                       (pinned host -> staging slot)
+    compute stream   forward + backward(chunk i)          (the same C-ABI calls as MSDeformAttnFunction)
+    copy-out stream  D2H(chunk i-1)                       (results -> pinned host)
+
+PCIe is full duplex, so a step costs about max(H2D, D2H) instead of H2D + kernels + D2H.  Results are
+bit-identical to one call over the whole batch (chunking by frames changes no summation order).
+
+No CPU fallback: without a CUDA device (or the library) this raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import msda_ext
+
+_SLOTS = 3   # staging slots for the inputs: one being filled, one being computed on, one slack
+
+
+def chunk_ranges(n_frames: int, frames_per_chunk: int) -> List[Tuple[int, int]]:
+    """[start, stop) frame ranges of the pipeline's chunks; the last one may be short."""
+    if n_frames < 0 or frames_per_chunk <= 0:
+        raise ValueError("n_frames must be >= 0 and frames_per_chunk > 0")
+    return [(s, min(s + frames_per_chunk, n_frames)) for s in range(0, n_frames, frames_per_chunk)]
+
+
+def _require_pinned(named: Sequence[Tuple[str, torch.Tensor]]) -> None:
+    for name, t in named:
+        if t.is_cuda:
+            raise RuntimeError(f"{name} is a CUDA tensor: this entry point takes host buffers "
+                               f"(use MSDeformAttnFunction for device tensors)")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_pinned():
+            raise RuntimeError(f"{name} must be in pinned host memory (tensor.pin_memory()) for asynchronous copies")
+
+
+class HostFramePipeline:
+    """Reusable pipeline state (streams, staging slots, events) for one device.
+
+        pipe = HostFramePipeline("cuda:0", frames_per_chunk=2)
+        out, grad_value, grad_loc, grad_attn = pipe.forward_backward(
+            value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output)
+
+    All six tensors except the two small int64 ones are pinned host tensors with the layouts of
+    ``MSDeformAttnFunction``; the four results are pinned host tensors (pass ``results=`` to reuse
+    buffers).  The call returns once everything is queued; the results are complete after the current
+    stream (which is made to wait for the pipeline) has been synchronised.
+    """
+
+    def __init__(self, device="cuda:0", frames_per_chunk: int = 2, im2col_step: int = 64):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HostFramePipeline needs a CUDA device: there is no CPU path for the op")
+        self.device = torch.device(device)
+        self.frames_per_chunk = int(frames_per_chunk)
+        self.im2col_step = im2col_step
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
+        self._slots: Optional[List[Dict[str, torch.Tensor]]] = None
+        self._slot_key = None
+        self._slot_free = [None] * _SLOTS      # event: the compute that last read the slot has finished
+        self._meta: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.launches = 0                      # kernels launched by the last call
+
+    # -- small int64 tables: resident on the device, cached by content
+    def _tables(self, spatial_shapes, level_start_index):
+        key = (tuple(spatial_shapes.flatten().tolist()), tuple(level_start_index.flatten().tolist()))
+        if key not in self._meta:
+            self._meta[key] = (spatial_shapes.to(self.device, torch.int64).contiguous(),
+                               level_start_index.to(self.device, torch.int64).contiguous())
+        return self._meta[key]
+
+    def _staging(self, named):
+        key = tuple((n, tuple(t.shape[1:]), t.dtype) for n, t in named)
+        if self._slots is None or self._slot_key != key:
+            fpc = self.frames_per_chunk
+            self._slots = [{n: torch.empty((fpc,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+                            for n, t in named} for _ in range(_SLOTS)]
+            self._slot_key = key
+            self._slot_free = [None] * _SLOTS
+        return self._slots
+
+    def forward_backward(self, value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                         grad_output, results: Optional[Sequence[torch.Tensor]] = None):
+        named = [("value", value), ("sampling_locations", sampling_locations),
+                 ("attention_weights", attention_weights), ("grad_output", grad_output)]
+        _require_pinned(named)
+        N, S, M, D = value.shape
+        Lq = sampling_locations.shape[1]
+        if grad_output.shape[0] != N or sampling_locations.shape[0] != N or attention_weights.shape[0] != N:
+            raise RuntimeError("value, sampling_locations, attention_weights and grad_output must hold the same frames")
+        if results is None:
+            results = (torch.empty((N, Lq, M * D), dtype=value.dtype).pin_memory(),
+                       torch.empty_like(value).pin_memory(),
+                       torch.empty_like(sampling_locations).pin_memory(),
+                       torch.empty_like(attention_weights).pin_memory())
+        else:
+            _require_pinned([(f"results[{i}]", r) for i, r in enumerate(results)])
+        out_h, gv_h, gl_h, ga_h = results
+        shapes_d, lsi_d = self._tables(spatial_shapes, level_start_index)
+        slots = self._staging(named)
+
+        with torch.cuda.device(self.device):
+            caller = torch.cuda.current_stream()
+            start = torch.cuda.Event()
+            start.record(caller)
+            self.s_in.wait_event(start)        # host buffers written by work queued on the caller's stream
+            self.s_out.wait_event(start)       # ... and result buffers it may still be reading
+            self.launches = 0
+            last_out = None
+            for i, (lo, hi) in enumerate(chunk_ranges(N, self.frames_per_chunk)):
+                slot = slots[i % _SLOTS]
+                n = hi - lo
+                with torch.cuda.stream(self.s_in):
+                    if self._slot_free[i % _SLOTS] is not None:
+                        self.s_in.wait_event(self._slot_free[i % _SLOTS])
+                    for name, t in named:
+                        slot[name][:n].copy_(t[lo:hi], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self.s_in)
+                with torch.cuda.stream(self.s_run):
+                    self.s_run.wait_event(ready)
+                    a = (slot["value"][:n], shapes_d, lsi_d, slot["sampling_locations"][:n], slot["attention_weights"][:n])
+                    out, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True)
+                    self.launches += msda_ext.last_launch_count()
+                    gv, gl, ga = msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index)
+                    self.launches += msda_ext.last_launch_count()
+                    done = torch.cuda.Event()
+                    done.record(self.s_run)
+                    self._slot_free[i % _SLOTS] = done
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(done)
+                    for dst, src in ((out_h, out), (gv_h, gv), (gl_h, gl), (ga_h, ga)):
+                        src.record_stream(self.s_out)      # allocated on the compute stream, read here
+                        dst[lo:hi].copy_(src, non_blocking=True)
+                    last_out = torch.cuda.Event()
+                    last_out.record(self.s_out)
+            if last_out is not None:
+                caller.wait_event(last_out)    # synchronising the caller's stream now covers the whole pipeline
+        return out_h, gv_h, gl_h, ga_h
+
+
+def forward_backward_host(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                          grad_output, device="cuda:0", frames_per_chunk: int = 2, im2col_step: int = 64):
+    """One-shot convenience wrapper around ``HostFramePipeline`` (synchronises before returning)."""
+    pipe = HostFramePipeline(device, frames_per_chunk, im2col_step)
+    res = pipe.forward_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                                grad_output)
+    torch.cuda.current_stream(pipe.device).synchronize()
+    return res

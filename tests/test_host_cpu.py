@@ -103,3 +103,16 @@ def test_synthetic_inputs():
     assert (fwd, bwd) == (81600 * 3584, 81600 * 6144)
     fwd, bwd = algorithmic_bytes(16, 5100, 8, 32, 4, 5100, 4, 2, 4)
     assert (fwd, bwd) == (81600 * 2560, 81600 * 4608)
+
+
+def test_host_pipeline_chunk_plan_and_no_cpu_path():
+    from neurips2023_soc_b200 import host_frames
+    assert host_frames.chunk_ranges(16, 2) == [(2 * i, 2 * i + 2) for i in range(8)]
+    assert host_frames.chunk_ranges(5, 2) == [(0, 2), (2, 4), (4, 5)]
+    assert host_frames.chunk_ranges(0, 4) == []
+    assert host_frames.chunk_ranges(3, 8) == [(0, 3)]
+    with pytest.raises(ValueError):
+        host_frames.chunk_ranges(4, 0)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            host_frames.HostFramePipeline("cuda:0")
