@@ -25,7 +25,7 @@ import torch
 
 from . import msda_ext
 
-_SLOTS = 3   # staging slots for the inputs: one being filled, one being computed on, one slack
+_SLOTS = 3   # buffer sets in flight: one being filled, one being computed on, one being drained
 
 
 def chunk_ranges(n_frames: int, frames_per_chunk: int) -> List[Tuple[int, int]]:
@@ -46,10 +46,32 @@ def _require_pinned(named: Sequence[Tuple[str, torch.Tensor]]) -> None:
             raise RuntimeError(f"{name} must be in pinned host memory (tensor.pin_memory()) for asynchronous copies")
 
 
+def ramped_chunk_ranges(n_frames: int, frames_per_chunk: int) -> List[Tuple[int, int]]:
+    """Chunks that start and end small (1, 1, 2, 4, ... up to ``frames_per_chunk`` and back down): the first
+    copy-in and the last copy-out are the only transfers nothing else can hide, so they are kept short, while
+    the chunks in between are large enough to amortise launch and queueing costs."""
+    if n_frames < 0 or frames_per_chunk <= 0:
+        raise ValueError("n_frames must be >= 0 and frames_per_chunk > 0")
+    head, size = [], 1
+    while size < frames_per_chunk:
+        head.append(size)
+        size = size * 2 if len(head) > 1 else 1
+    if not head or 2 * sum(head) + frames_per_chunk > n_frames:
+        return chunk_ranges(n_frames, frames_per_chunk)
+    middle = n_frames - 2 * sum(head)
+    sizes = head + [frames_per_chunk] * (middle // frames_per_chunk) + \
+        ([middle % frames_per_chunk] if middle % frames_per_chunk else []) + head[::-1]
+    out, s0 = [], 0
+    for sz in sizes:
+        out.append((s0, s0 + sz))
+        s0 += sz
+    return out
+
+
 class HostFramePipeline:
     """Reusable pipeline state (streams, staging slots, events) for one device.
 
-        pipe = HostFramePipeline("cuda:0", frames_per_chunk=2)
+        pipe = HostFramePipeline("cuda:0", frames_per_chunk=4)
         out, grad_value, grad_loc, grad_attn = pipe.forward_backward(
             value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output)
 
@@ -59,17 +81,22 @@ class HostFramePipeline:
     stream (which is made to wait for the pipeline) has been synchronised.
     """
 
-    def __init__(self, device="cuda:0", frames_per_chunk: int = 2, im2col_step: int = 64):
+    def __init__(self, device="cuda:0", frames_per_chunk: int = 4, im2col_step: int = 64, ramp: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("HostFramePipeline needs a CUDA device: there is no CPU path for the op")
         self.device = torch.device(device)
         self.frames_per_chunk = int(frames_per_chunk)
         self.im2col_step = im2col_step
+        self.ramp = ramp
+        self.trace = False                     # True: time every stage of the next call with CUDA events
+        self._marks: List[Tuple[int, str, torch.cuda.Event, torch.cuda.Event]] = []
+        self._t0: Optional[torch.cuda.Event] = None
         with torch.cuda.device(self.device):
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
         self._slots: Optional[List[Dict[str, torch.Tensor]]] = None
         self._slot_key = None
-        self._slot_free = [None] * _SLOTS      # event: the compute that last read the slot has finished
+        self._computed = [None] * _SLOTS
+        self._drained = [None] * _SLOTS
         self._meta: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self.launches = 0                      # kernels launched by the last call
 
@@ -82,13 +109,30 @@ class HostFramePipeline:
         return self._meta[key]
 
     def _staging(self, named):
+        """The device side of the pipeline: per slot, the chunk's inputs, its four results, the backward's
+        workspace and the forward's index -- allocated once per problem shape, so that a step makes no
+        allocator call (a cudaMalloc in the loop would serialise the three streams)."""
         key = tuple((n, tuple(t.shape[1:]), t.dtype) for n, t in named)
         if self._slots is None or self._slot_key != key:
-            fpc = self.frames_per_chunk
-            self._slots = [{n: torch.empty((fpc,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-                            for n, t in named} for _ in range(_SLOTS)]
+            fpc, dev = self.frames_per_chunk, self.device
+            value, loc = named[0][1], named[1][1]
+            M, D = value.shape[2], value.shape[3]
+            Lq = loc.shape[1]
+            self._slots = []
+            for _ in range(_SLOTS):
+                slot = {n: torch.empty((fpc,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for n, t in named}
+                slot["out"] = torch.empty((fpc, Lq, M * D), dtype=value.dtype, device=dev)
+                slot["gv"] = torch.empty_like(slot["value"])
+                slot["gl"] = torch.empty_like(slot["sampling_locations"])
+                slot["ga"] = torch.empty_like(slot["attention_weights"])
+                slot["ws"] = torch.empty(max(16, msda_ext.backward_workspace_bytes(slot["value"], slot["sampling_locations"])),
+                                         dtype=torch.uint8, device=dev)
+                slot["index"] = torch.empty(max(16, msda_ext.forward_index_bytes(slot["value"], slot["sampling_locations"])),
+                                            dtype=torch.uint8, device=dev)
+                self._slots.append(slot)
             self._slot_key = key
-            self._slot_free = [None] * _SLOTS
+            self._computed = [None] * _SLOTS   # event: the kernels that last read the slot's inputs have finished
+            self._drained = [None] * _SLOTS    # event: the D2H copies that last read the slot's results have finished
         return self._slots
 
     def forward_backward(self, value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
@@ -113,46 +157,75 @@ class HostFramePipeline:
 
         with torch.cuda.device(self.device):
             caller = torch.cuda.current_stream()
-            start = torch.cuda.Event()
+            start = torch.cuda.Event(enable_timing=self.trace)
             start.record(caller)
+            self._marks, self._t0 = [], start
+
+            def mark(stream):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                return e
             self.s_in.wait_event(start)        # host buffers written by work queued on the caller's stream
             self.s_out.wait_event(start)       # ... and result buffers it may still be reading
             self.launches = 0
             last_out = None
-            for i, (lo, hi) in enumerate(chunk_ranges(N, self.frames_per_chunk)):
-                slot = slots[i % _SLOTS]
+            plan = (ramped_chunk_ranges if self.ramp else chunk_ranges)(N, self.frames_per_chunk)
+            for i, (lo, hi) in enumerate(plan):
+                k = i % _SLOTS
+                slot = slots[k]
                 n = hi - lo
+                if self._computed[k] is not None:
+                    self.s_in.wait_event(self._computed[k])
+                b0 = mark(self.s_in) if self.trace else None
                 with torch.cuda.stream(self.s_in):
-                    if self._slot_free[i % _SLOTS] is not None:
-                        self.s_in.wait_event(self._slot_free[i % _SLOTS])
                     for name, t in named:
                         slot[name][:n].copy_(t[lo:hi], non_blocking=True)
-                    ready = torch.cuda.Event()
-                    ready.record(self.s_in)
+                if self.trace:
+                    self._marks.append((i, "h2d", b0, mark(self.s_in)))
+                ready = torch.cuda.Event()
+                ready.record(self.s_in)
+                self.s_run.wait_event(ready)
+                if self._drained[k] is not None:
+                    self.s_run.wait_event(self._drained[k])
+                b0 = mark(self.s_run) if self.trace else None
                 with torch.cuda.stream(self.s_run):
-                    self.s_run.wait_event(ready)
                     a = (slot["value"][:n], shapes_d, lsi_d, slot["sampling_locations"][:n], slot["attention_weights"][:n])
-                    out, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True)
+                    _, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True,
+                                                               out=slot["out"][:n], index_buf=slot["index"])
                     self.launches += msda_ext.last_launch_count()
-                    gv, gl, ga = msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index)
+                    msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index,
+                                                     grads=(slot["gv"][:n], slot["gl"][:n], slot["ga"][:n]),
+                                                     workspace=slot["ws"])
                     self.launches += msda_ext.last_launch_count()
-                    done = torch.cuda.Event()
-                    done.record(self.s_run)
-                    self._slot_free[i % _SLOTS] = done
+                if self.trace:
+                    self._marks.append((i, "run", b0, mark(self.s_run)))
+                done = torch.cuda.Event()
+                done.record(self.s_run)
+                self._computed[k] = done
+                self.s_out.wait_event(done)
+                b0 = mark(self.s_out) if self.trace else None
                 with torch.cuda.stream(self.s_out):
-                    self.s_out.wait_event(done)
-                    for dst, src in ((out_h, out), (gv_h, gv), (gl_h, gl), (ga_h, ga)):
-                        src.record_stream(self.s_out)      # allocated on the compute stream, read here
-                        dst[lo:hi].copy_(src, non_blocking=True)
-                    last_out = torch.cuda.Event()
-                    last_out.record(self.s_out)
+                    for dst, src in ((out_h, "out"), (gv_h, "gv"), (gl_h, "gl"), (ga_h, "ga")):
+                        dst[lo:hi].copy_(slot[src][:n], non_blocking=True)
+                if self.trace:
+                    self._marks.append((i, "d2h", b0, mark(self.s_out)))
+                last_out = torch.cuda.Event()
+                last_out.record(self.s_out)
+                self._drained[k] = last_out
             if last_out is not None:
                 caller.wait_event(last_out)    # synchronising the caller's stream now covers the whole pipeline
         return out_h, gv_h, gl_h, ga_h
 
 
+    def timeline(self) -> List[Tuple[int, str, float, float]]:
+        """(chunk, stage, begin ms, end ms) of the last traced call, relative to its start on the caller's
+        stream; stages are "h2d", "run" and "d2h".  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        return [(i, st, self._t0.elapsed_time(b), self._t0.elapsed_time(e)) for i, st, b, e in self._marks]
+
+
 def forward_backward_host(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
-                          grad_output, device="cuda:0", frames_per_chunk: int = 2, im2col_step: int = 64):
+                          grad_output, device="cuda:0", frames_per_chunk: int = 4, im2col_step: int = 64):
     """One-shot convenience wrapper around ``HostFramePipeline`` (synchronises before returning)."""
     pipe = HostFramePipeline(device, frames_per_chunk, im2col_step)
     res = pipe.forward_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,

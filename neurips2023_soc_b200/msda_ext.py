@@ -68,22 +68,42 @@ def _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     return (N, S, M, D, L, Lq, P), _DTYPE[value.dtype], _DTYPE[sampling_loc.dtype]
 
 
+def _into(buf, shape, dtype, device, what):
+    """A caller-owned result buffer (``out=`` style, beyond the reference signature) viewed with the result's shape."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    _require(isinstance(buf, torch.Tensor) and buf.is_cuda and buf.device == device and buf.dtype == dtype
+             and buf.is_contiguous() and buf.numel() == n,
+             f"{what} must be a contiguous {dtype} tensor of {n} elements on {device}")
+    return buf.view(shape)
+
+
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                           im2col_step: int, flags: int | None = None, want_index: bool = False):
+                           im2col_step: int, flags: int | None = None, want_index: bool = False,
+                           out=None, index_buf=None):
     """``want_index=True`` (not part of the reference signature) also returns the index the matching
-    backward can use -- and uses up: ``(output, index)``, see msda_forward_indexed in include/msda_b200.h."""
+    backward can use -- and uses up: ``(output, index)``, see msda_forward_indexed in include/msda_b200.h.
+    ``out`` / ``index_buf``: caller-owned buffers to write into instead of allocating (callers that run the op
+    in a loop on their own streams, e.g. host_frames.HostFramePipeline)."""
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)])
     dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     N, S, M, D, L, Lq, P = dims
     lib = _lib.load()
     with torch.cuda.device(value.device):
-        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        out = (torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device) if out is None
+               else _into(out, (N, Lq, M * D), value.dtype, value.device, "out"))
         stream = torch.cuda.current_stream().cuda_stream
         index, index_ptr, index_bytes = None, None, 0
         if want_index:
             index_bytes = int(lib.msda_index_bytes(*dims))
-            index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
+            if index_buf is None:
+                index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
+            else:
+                _require(index_buf.is_cuda and index_buf.dtype == torch.uint8 and index_buf.is_contiguous()
+                         and index_buf.numel() >= index_bytes, f"index_buf must hold {index_bytes} bytes")
+                index = index_buf[:index_bytes]
             index_ptr = index.data_ptr()
         _lib.check(lib.msda_forward_indexed(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
@@ -92,8 +112,23 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return (out, index) if want_index else out
 
 
+def backward_workspace_bytes(value, sampling_loc) -> int:
+    """msda_backward_workspace_bytes for a call with these tensors (for callers that own the workspace)."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    return int(_lib.load().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, _DTYPE[value.dtype], _DTYPE[sampling_loc.dtype]))
+
+
+def forward_index_bytes(value, sampling_loc) -> int:
+    """msda_index_bytes for a call with these tensors."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_loc.shape
+    return int(_lib.load().msda_index_bytes(N, S, M, D, L, Lq, P))
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step: int, flags: int | None = None, index=None) -> List[torch.Tensor]:
+                            im2col_step: int, flags: int | None = None, index=None, grads=None,
+                            workspace=None) -> List[torch.Tensor]:
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
     dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
@@ -103,11 +138,21 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     lib = _lib.load()
     flags = DEFAULT_FLAGS if flags is None else flags
     with torch.cuda.device(value.device):
-        grad_value = torch.empty_like(value)
-        grad_loc = torch.empty_like(sampling_loc)
-        grad_attn = torch.empty_like(attn_weight)
+        if grads is None:
+            grad_value = torch.empty_like(value)
+            grad_loc = torch.empty_like(sampling_loc)
+            grad_attn = torch.empty_like(attn_weight)
+        else:                                   # caller-owned result buffers
+            grad_value = _into(grads[0], value.shape, value.dtype, value.device, "grads[0]")
+            grad_loc = _into(grads[1], sampling_loc.shape, sampling_loc.dtype, value.device, "grads[1]")
+            grad_attn = _into(grads[2], attn_weight.shape, attn_weight.dtype, value.device, "grads[2]")
         ws_bytes = 0 if flags & _lib.FLAG_ATOMIC_GRAD_VALUE else int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+        if workspace is None:
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+        else:
+            _require(workspace.is_cuda and workspace.dtype == torch.uint8 and workspace.is_contiguous()
+                     and workspace.numel() >= ws_bytes, f"workspace must hold {ws_bytes} bytes")
+            ws = workspace
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.msda_backward_indexed(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),

@@ -456,19 +456,19 @@ def test_bf16_lane_layout_switch():
         assert rel_err(a[i], b[i].double().cpu().numpy()) <= 2e-2
 
 
-@pytest.mark.parametrize("frames_per_chunk", [1, 2, 3, 8])
-def test_host_frame_pipeline_matches_one_call(frames_per_chunk):
+@pytest.mark.parametrize("frames_per_chunk,ramp", [(1, False), (2, False), (2, True), (3, False), (8, True)])
+def test_host_frame_pipeline_matches_one_call(frames_per_chunk, ramp):
     """The host entry point (chunks of frames streamed over PCIe on three streams) returns the bits of
     one call over the whole batch, for ragged last chunks and when called again on the same state."""
     from neurips2023_soc_b200.host_frames import HostFramePipeline
-    x = make_inputs(N=5, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], dist="encoder", seed=11)
+    x = make_inputs(N=7, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], dist="encoder", seed=11)
     host = x.to("cpu", torch.bfloat16, torch.float32)
     pins = [t.pin_memory() for t in (host.value, host.sampling_locations, host.attention_weights, host.grad_output)]
     d = host.to(DEV)
     a = (d.value, d.spatial_shapes, d.level_start_index, d.sampling_locations, d.attention_weights)
     out, index = msda_ext.ms_deform_attn_forward(*a, 64, want_index=True)
     ref = [out] + msda_ext.ms_deform_attn_backward(*a, d.grad_output, 64, index=index)
-    pipe = HostFramePipeline(DEV, frames_per_chunk=frames_per_chunk)
+    pipe = HostFramePipeline(DEV, frames_per_chunk=frames_per_chunk, ramp=ramp)
     for _ in range(2):
         res = pipe.forward_backward(pins[0], host.spatial_shapes, host.level_start_index, pins[1], pins[2], pins[3])
         torch.cuda.current_stream().synchronize()

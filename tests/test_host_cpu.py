@@ -113,6 +113,12 @@ def test_host_pipeline_chunk_plan_and_no_cpu_path():
     assert host_frames.chunk_ranges(3, 8) == [(0, 3)]
     with pytest.raises(ValueError):
         host_frames.chunk_ranges(4, 0)
+    assert [b - a for a, b in host_frames.ramped_chunk_ranges(16, 4)] == [1, 1, 2, 4, 4, 2, 1, 1]
+    for n in range(0, 40):
+        for f in (1, 2, 3, 4, 8, 16):
+            c = host_frames.ramped_chunk_ranges(n, f)
+            assert [a for a, _ in c] == [0] * bool(c) + [b for _, b in c[:-1]]      # contiguous from 0
+            assert (c[-1][1] if c else 0) == n and all(0 < b - a <= f for a, b in c)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU path"):
             host_frames.HostFramePipeline("cuda:0")
