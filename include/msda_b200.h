@@ -80,6 +80,8 @@ enum msda_status {
 #define MSDA_FLAG_GENERIC 2u       /* force the any-D scalar kernels */
 #define MSDA_FLAG_ATOMIC_GRAD_VALUE 4u /* bench-only: fp32 red.global scatter (NOT deterministic) */
 #define MSDA_FLAG_BF16_VEC8 8u     /* A/B: 64-byte bf16 rows on 4 lanes x 128 bit instead of 8 x 64 bit */
+#define MSDA_FLAG_WALK_DENSE 16u   /* force the inverse-index pipeline for grad_value even when the call is small enough
+                                      for the direct shared-memory gather (decoder-shaped calls, Lq * P <= 512) */
 
 int msda_version(void);
 
@@ -105,7 +107,9 @@ int msda_forward_ex(const void *value, const int64_t *spatial_shapes, const int6
  * skips its own counting pass and CONSUMES the buffer (it advances the offsets in place; pass a
  * copy to run a second backward).  With index == NULL both calls behave like the plain ones.
  * The reference's autograd function has no such state (it saves inputs only,
- * ms_deform_attn_func.py:27); the index is a pure function of the saved inputs. */
+ * ms_deform_attn_func.py:27); the index is a pure function of the saved inputs.
+ * msda_index_bytes returns 0 for calls with so few queries per frame (4 * Lq * P <= 2048: decoder
+ * cross-attention) that the backward keeps no index at all; an index passed for such a call is ignored. */
 size_t msda_index_bytes(int N, int S, int M, int D, int L, int Lq, int P);
 
 int msda_forward_indexed(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,

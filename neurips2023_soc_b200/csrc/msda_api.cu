@@ -322,6 +322,7 @@ int launch_sort(const Params& p, cudaStream_t st) {
     k<<<persistent_grid(k, kThreads, items), kThreads, 0, st>>>(p);
     prof_end(st);
     MSDA_LAUNCHED("msda_bin_rank_sort_kernel");
+    if ((long long)p.Lq * p.LP <= kRankMax) return MSDA_OK;   // no sub-bin can hold more than the rank sort takes
     prof_begin(st, "msda_bin_sort_big_kernel");
     msda_bin_sort_big_kernel<CT><<<num_sms() * 2, kThreads, 0, st>>>(p);
     prof_end(st);
@@ -338,6 +339,27 @@ int launch_grad_value_walk(const Params& p, cudaStream_t st) {
     k<<<persistent_grid(k, kGThreads, tiles), kGThreads, 0, st>>>(p);
     prof_end(st);
     MSDA_LAUNCHED("msda_grad_value_walk_kernel");
+    return MSDA_OK;
+}
+
+int ceil_log2(long long x) {
+    int k = 0;
+    while ((1LL << k) < x) ++k;
+    return k;
+}
+
+template <typename T, typename TA, int VEC, int G>
+int launch_grad_value_direct(const Params& p, cudaStream_t st) {
+    prof_begin(st, "memset(grad_value)");
+    MSDA_CUDA(cudaMemsetAsync(p.grad_value, 0, (size_t)p.N * p.S * p.M * p.D * sizeof(T), st));
+    prof_end(st);
+    ++g_launches;
+    auto k = msda_grad_value_direct_kernel<T, TA, VEC, G>;
+    const int K = 1 << ceil_log2(4LL * p.Lq * p.P);
+    prof_begin(st, "msda_grad_value_direct_kernel");
+    k<<<persistent_grid(k, kThreads, (long long)p.N * p.M * p.L), kThreads, 0, st>>>(p, K < 4 ? 4 : K, ceil_log2((long long)p.Lq * p.P));
+    prof_end(st);
+    MSDA_LAUNCHED("msda_grad_value_direct_kernel");
     return MSDA_OK;
 }
 
@@ -399,6 +421,32 @@ int dispatch_bwd_sample_tile(const Params& p, const Plan& pl, int vdt, cudaStrea
     }
 }
 
+// Calls with few queries per frame (decoder cross-attention) skip the inverse index altogether: the
+// contributions of one (frame, head, level) fit in shared memory (msda_grad_value_direct_kernel).  The choice
+// depends on per-frame quantities only, so chunking a batch by frames never changes a result.
+bool direct_call(int S, int Lq, int P, unsigned flags) {
+    if (flags & (MSDA_FLAG_WALK_DENSE | MSDA_FLAG_ATOMIC_GRAD_VALUE | MSDA_FLAG_GENERIC)) return false;
+    if (4LL * Lq * P > kDirectMax) return false;
+    return ceil_log2(S) + ceil_log2((long long)Lq * P) + 2 <= 32;      // pixel | sample | corner in one 32-bit key
+}
+
+template <typename TA>
+int dispatch_grad_value_direct(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {
+    if (vdt == MSDA_F32) {
+        if constexpr (std::is_same<TA, float>::value) {
+            switch (pl.wg) {
+                case 4: return launch_grad_value_direct<float, float, 4, 4>(p, st);
+                case 8: return launch_grad_value_direct<float, float, 4, 8>(p, st);
+                default: return launch_grad_value_direct<float, float, 4, 16>(p, st);
+            }
+        }
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fp32 values need fp32 locations");
+    }
+    using B = __nv_bfloat16;
+    if (pl.wvec == 4) return pl.wg == 8 ? launch_grad_value_direct<B, TA, 4, 8>(p, st) : launch_grad_value_direct<B, TA, 4, 16>(p, st);
+    return launch_grad_value_direct<B, TA, 8, 16>(p, st);
+}
+
 int dispatch_grad_value_walk(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {
     if (vdt == MSDA_F32) {
         switch (pl.wg) {
@@ -450,6 +498,13 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
     bool tile = pl.tile;
     if constexpr (std::is_same<T, double>::value || std::is_same<T, __half>::value) tile = false;
     const bool atomic_arm = (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) != 0;
+    if (tile && direct_call(p.S, p.Lq, p.P, p.flags)) {
+        if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
+            p.entries = nullptr;                 // part A keeps no index entries
+            if ((rc = dispatch_bwd_sample_tile<TA>(p, pl, vdt, st))) return rc;
+            return dispatch_grad_value_direct<TA>(p, pl, vdt, st);
+        }
+    }
     if (!atomic_arm) {
         // sub-bin offsets: handed over by the forward, or counted and scanned here
         if (index) {
@@ -523,6 +578,7 @@ int msda_profile_read(char* names, size_t names_cap, float* ms, int cap) {
 size_t msda_index_bytes(int N, int S, int M, int D, int L, int Lq, int P) {
     (void)D;
     if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || Lq <= 0 || P <= 0) return 0;
+    if (direct_call(S, Lq, P, 0)) return 0;      // few queries per frame: the backward keeps no index at all
     return index_bytes(N, S, M, L, Lq, P);
 }
 
@@ -554,6 +610,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
     p.id_shift = id_shift_for(p.LP);
     p.flags = flags;
     p.sb_max = sub_bin_bound(S, L, Lq, P);
+    if (index && msda_index_bytes(N, S, M, D, L, Lq, P) == 0) index = nullptr;   // no handoff for this shape
     if (index) {
         const size_t need = index_bytes(N, S, M, L, Lq, P);
         if (index_size < need || !aligned16(index))
@@ -673,6 +730,7 @@ int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, cons
     if (need_ws && !aligned16(workspace))
         return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
     const size_t table_bytes = index_bytes(N, S, M, L, Lq, P);
+    if (index && msda_index_bytes(N, S, M, D, L, Lq, P) == 0) index = nullptr;   // no handoff for this shape
     if (index && index_size < table_bytes)
         return fail(MSDA_ERR_WORKSPACE, "index buffer of %zu bytes required, got %zu", table_bytes, index_size);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

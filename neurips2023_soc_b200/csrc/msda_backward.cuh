@@ -877,6 +877,131 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
     }
 }
 
+// Direct gather for calls with few queries per frame (decoder cross-attention: Lq = 5 .. 100 over thousands of
+// pixels, /root/reference/models/deformable_transformer.py:330-347).  The inverse index costs five launches that
+// all scale with the number of BINS; here nothing does.  grad_value is cleared with a memset and one CTA per
+// (frame, head, level) handles that level's Lq*P samples entirely in shared memory:
+//   1. every sample yields up to four contributions (key, weight): key = pixel | sample | corner, weight =
+//      bilinear weight * attention weight (same geometry rules as everywhere, msda_common.cuh: locate);
+//   2. a bitonic network sorts them by key -- all contributions to one pixel become adjacent, in ascending
+//      (sample, corner) order, which fixes the summation order as a pure function of the inputs;
+//   3. a group of G lanes per touched pixel sums  weight * grad_output[query]  over its run and stores the row.
+// No atomics on floating-point data, no workspace; bit-identical from run to run.
+constexpr int kDirectMax = 2048;    // contributions (4 per sample) of one (frame, head, level) held in shared memory
+
+template <typename T, typename TA, int VEC, int G>
+__global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const Params p, const int K, const int id_bits) {
+    constexpr int NG = kThreads / G;
+    constexpr int B = 4;                                  // grad_output rows in flight per lane
+    __shared__ Level lv[kMaxLevels];
+    __shared__ int s_sb, s_sq;
+    __shared__ uint32_t s_key[kDirectMax];
+    __shared__ float s_w[kDirectMax];
+    __shared__ uint16_t s_head[kDirectMax];               // first contribution of every touched pixel
+    __shared__ int s_nhead;
+    load_levels(p, lv, &s_sb, &s_sq);
+    const TA* __restrict__ loc = static_cast<const TA*>(p.loc);
+    const TA* __restrict__ attn = static_cast<const TA*>(p.attn);
+    const T* __restrict__ gout = static_cast<const T*>(p.grad_out);
+    T* __restrict__ gval = static_cast<T*>(p.grad_value);
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    const int nsamp = p.Lq * p.P;                         // samples of one (frame, head, level)
+    const int pshift = id_bits + 2;
+    const uint32_t idmask = (1u << id_bits) - 1u;
+    const int items = p.N * p.M * p.L;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int l = it % p.L;
+        const int nm = it / p.L;
+        const int m = nm % p.M, n = nm / p.M;
+        const Level L_ = lv[l];
+        if (threadIdx.x == 0) s_nhead = 0;
+        // 1. contributions
+        for (int i = threadIdx.x; i < K / 4; i += kThreads) {
+            uint32_t key[4] = {~0u, ~0u, ~0u, ~0u};
+            float w[4] = {0.f, 0.f, 0.f, 0.f};
+            if (i < nsamp) {
+                const int q = i / p.P, pt = i - q * p.P;
+                const size_t si = (((size_t)n * p.Lq + q) * p.M + m) * p.LP + l * p.P + pt;
+                const XY<float> xy = load_xy(loc + 2 * si);
+                const float a = (float)ld_stream(attn + si);
+                const Sample<float> sm = locate(xy.x, xy.y, L_.H, L_.W);
+                if (sm.ok) {
+                    int pix[4];
+                    corner_pixels(sm, L_, pix);           // level_start + h*W + w, or -1 outside the map
+                    const float hh = 1.f - sm.lh, hw = 1.f - sm.lw;
+                    const float cw[4] = {hh * hw, hh * sm.lw, sm.lh * hw, sm.lh * sm.lw};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (pix[c] >= 0) {
+                            key[c] = ((uint32_t)(pix[c] - L_.start) << pshift) | ((uint32_t)i << 2) | (uint32_t)c;
+                            w[c] = cw[c] * a;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                s_key[4 * i + c] = key[c];
+                s_w[4 * i + c] = w[c];
+            }
+        }
+        __syncthreads();
+        // 2. bitonic sort by key, the weight rides along
+        for (int k = 2; k <= K; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < K; t += kThreads) {
+                    const int u = t ^ j;
+                    if (u > t) {
+                        const uint32_t a0 = s_key[t], a1 = s_key[u];
+                        if ((a0 > a1) == ((t & k) == 0)) {
+                            s_key[t] = a1; s_key[u] = a0;
+                            const float w0 = s_w[t];
+                            s_w[t] = s_w[u]; s_w[u] = w0;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // 3. runs of equal pixel (which group takes which run does not matter: runs are independent)
+        for (int t = threadIdx.x; t < K; t += kThreads) {
+            const uint32_t kt = s_key[t];
+            if (kt != ~0u && (t == 0 || (s_key[t - 1] >> pshift) != (kt >> pshift)))
+                s_head[atomicAdd(&s_nhead, 1)] = (uint16_t)t;
+        }
+        __syncthreads();
+        const int nhead = s_nhead;
+        const T* __restrict__ gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
+        const size_t qstride = (size_t)p.M * p.D;
+        for (int r = grp; r < nhead; r += NG) {
+            int t = s_head[r];
+            const uint32_t pix = s_key[t] >> pshift;
+            float acc[VEC];
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+            while (t < K && (s_key[t] >> pshift) == pix) {
+                float g[B][VEC], w[B];
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                    const bool on = t + j < K && (s_key[t + j] >> pshift) == pix;
+                    w[j] = on ? s_w[t + j] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) g[j][c] = 0.f;
+                    if (on) load_row<T, VEC>(gbase + (size_t)(((s_key[t + j] >> 2) & idmask) / p.P) * qstride, g[j]);
+                }
+                // contributions past the run's end carry weight 0 and a zero row: adding +0 changes nothing
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[j], g[j][c], acc[c]);
+                t += B;
+            }
+            store_row<T, VEC>(gval + (((size_t)n * p.S + L_.start + pix) * p.M + m) * p.D + gl * VEC, acc);
+        }
+        __syncthreads();      // shared arrays are rewritten by the next item
+    }
+}
+
 // Any-D / any-dtype fallback: one warp per grad_value row, lanes stride the channels.
 template <typename T, typename CT>
 __global__ void __launch_bounds__(kThreads) msda_grad_value_generic_kernel(const Params p) {

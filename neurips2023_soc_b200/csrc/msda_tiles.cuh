@@ -158,7 +158,7 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
                     const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]) + 1;
                     if constexpr (MODE == kIndexCount) {
                         atomicAdd(p.bin_off + b, 1u);
-                    } else {
+                    } else if (p.entries != nullptr) {   // null: the direct gather follows, no index is kept
                         const uint32_t slot = atomicAdd(p.bin_off + b, 1u);
                         uint4 e;
                         e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;

@@ -191,7 +191,7 @@ class HostFramePipeline:
                 with torch.cuda.stream(self.s_run):
                     a = (slot["value"][:n], shapes_d, lsi_d, slot["sampling_locations"][:n], slot["attention_weights"][:n])
                     _, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True,
-                                                               out=slot["out"][:n], index_buf=slot["index"])
+                                                               out=slot["out"][:n], index_buf=slot["index"])   # None for small calls
                     self.launches += msda_ext.last_launch_count()
                     msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index,
                                                      grads=(slot["gv"][:n], slot["gl"][:n], slot["ga"][:n]),

@@ -97,14 +97,15 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
         stream = torch.cuda.current_stream().cuda_stream
         index, index_ptr, index_bytes = None, None, 0
         if want_index:
-            index_bytes = int(lib.msda_index_bytes(*dims))
-            if index_buf is None:
+            index_bytes = int(lib.msda_index_bytes(*dims))     # 0: calls this small keep no index (direct gather)
+            if index_bytes and index_buf is None:
                 index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
-            else:
+            elif index_bytes:
                 _require(index_buf.is_cuda and index_buf.dtype == torch.uint8 and index_buf.is_contiguous()
                          and index_buf.numel() >= index_bytes, f"index_buf must hold {index_bytes} bytes")
                 index = index_buf[:index_bytes]
-            index_ptr = index.data_ptr()
+            if index is not None:
+                index_ptr = index.data_ptr()
         _lib.check(lib.msda_forward_indexed(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), out.data_ptr(), index_ptr, index_bytes,
@@ -200,8 +201,9 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
         index, index_ptr, index_bytes = None, None, 0
         if want_index:
             index_bytes = int(lib.msda_index_bytes(*dims))
-            index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
-            index_ptr = index.data_ptr()
+            if index_bytes:
+                index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
+                index_ptr = index.data_ptr()
         _lib.check(lib.msda_forward_fused(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
             sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), loc.data_ptr(), attn.data_ptr(),

@@ -477,3 +477,47 @@ def test_host_frame_pipeline_matches_one_call(frames_per_chunk, ramp):
             assert got.is_pinned() and torch.equal(got, want.cpu())
     with pytest.raises(RuntimeError, match="pinned"):
         pipe.forward_backward(host.value, host.spatial_shapes, host.level_start_index, pins[1], pins[2], pins[3])
+
+
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                      (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("kw", [dict(N=3, dist="decoder", Lq=20), dict(N=2, dist="decoder", Lq=5),
+                                dict(N=2, dist="decoder", Lq=128), dict(N=1, dist="decoder", Lq=1),
+                                dict(N=2, dist="uniform", Lq=100),
+                                dict(N=2, dist="uniform", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], Lq=64, P=8),
+                                dict(N=1, dist="uniform", shapes=[(9, 11), (4, 5)], M=3, D=64, Lq=60, P=8),
+                                dict(N=2, dist="uniform", shapes=[(7, 9)], M=2, D=16, Lq=33, P=4)])
+def test_grad_value_gathers_agree(kw, vdt, adt):
+    """grad_value has two routes: the inverse-index pipeline (count / scan / fill / sort / walk) and, for calls
+    with few queries per frame (4 * Lq * P <= 2048: decoder cross-attention), a direct gather that sorts one
+    (frame, head, level)'s contributions in shared memory.  Forced either way, both must match the oracle and
+    leave grad_loc / grad_attn untouched; the direct one must be bit-reproducible and is the default here."""
+    if vdt == torch.float32 and adt != torch.float32:
+        pytest.skip("fp32 values take fp32 locations")
+    x = make_inputs(seed=17, **kw)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    dense = run_op(*a, vdt, adt, flags=_lib.FLAG_WALK_DENSE)
+    direct = run_op(*a, vdt, adt)
+    direct2 = run_op(*a, vdt, adt)
+    v, lo, at, go = dense[4]
+    r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
+    tol = TOL[vdt]
+    assert rel_err(dense[1], r_gv) <= tol and rel_err(direct[1], r_gv) <= tol
+    assert torch.equal(direct[1], direct2[1])
+    for i in (0, 2, 3):
+        assert torch.equal(dense[i], direct[i])
+    N, S, M, D = x.value.shape
+    Lq, L, P = x.sampling_locations.shape[1], x.sampling_locations.shape[3], x.sampling_locations.shape[4]
+    assert _lib.load().msda_index_bytes(N, S, M, D, L, Lq, P) == 0       # no index handoff for these shapes
+    assert _lib.load().msda_index_bytes(N, S, M, D, L, 600, P) > 0
+
+
+def test_direct_gather_is_frame_independent():
+    """The gather is chosen from per-frame quantities only: a frame's gradients do not depend on its batch."""
+    x = make_inputs(N=4, dist="decoder", Lq=20, seed=23)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    full = run_op(*a, torch.float32, torch.float32)
+    one = run_op(x.value[2:3], x.spatial_shapes, x.level_start_index, x.sampling_locations[2:3],
+                 x.attention_weights[2:3], x.grad_output[2:3], torch.float32, torch.float32)
+    for i in range(4):
+        assert torch.equal(full[i][2:3], one[i])

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--decoder", action="store_true", help="also time decoder cross-attention shapes (Lq = 5 / 20 / 300)")
     args = ap.parse_args()
     dev = "cuda:0"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -104,6 +105,36 @@ def main():
                 del x, a
             del base
             torch.cuda.empty_cache()
+    # decoder cross-attention shapes (BASELINE.json configs[1] and [3]): few queries per frame over the A2D pyramid
+    if args.decoder:
+        for N, Lq in ((16, 20), (2, 20), (36, 5), (36, 20), (16, 300)):
+            base = make_inputs(N=N, Lq=Lq, dist="decoder", seed=Lq)
+            S = base.value.shape[1]
+            for tag, vdt, adt in (("fp32", torch.float32, torch.float32), ("bf16", torch.bfloat16, torch.float32)):
+                x = base.to(dev, vdt, adt)
+                a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
+                f_med, _ = timed(lambda: msda_ext.ms_deform_attn_forward(*a, 64), args.iters, flush)
+                fi_med, _ = timed(lambda: msda_ext.ms_deform_attn_forward(*a, 64, want_index=True), args.iters, flush)
+
+                def pair():
+                    _, index = msda_ext.ms_deform_attn_forward(*a, 64, want_index=True)
+                    return msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64, index=index)
+                p_med, _ = timed(pair, args.iters, flush)
+                row = dict(tokens=S, P=4, dtype=tag, N=N, Lq=Lq, kind="decoder", fwd_us=f_med, bwd_us=p_med - fi_med,
+                           fwdbwd_us=p_med, fwdbwd_Mq_s=N * Lq / p_med)
+                if tag == "fp32" and ref is not None:
+                    rf, _ = timed(lambda: ref.ms_deform_attn_forward(*a, 64), args.iters, flush)
+                    rb, _ = timed(lambda: ref.ms_deform_attn_backward(*a, x.grad_output, 64), args.iters, flush)
+                    out = msda_ext.ms_deform_attn_forward(*a, 64)
+                    grads = pair()
+                    r_out = ref.ms_deform_attn_forward(*a, 64)
+                    r_grads = ref.ms_deform_attn_backward(*a, x.grad_output, 64)
+                    errs = [float((g - r).abs().max() / max(1.0, float(r.abs().max())))
+                            for g, r in zip([out] + list(grads), [r_out] + list(r_grads))]
+                    row.update(ref_cuda_fwd_us=rf, ref_cuda_bwd_us=rb, speedup_fwd=rf / f_med,
+                               speedup_bwd=rb / (p_med - fi_med), max_err_vs_ref_cuda=max(errs))
+                rows.append(row)
+                print(json.dumps(row), flush=True)
     with open("gpurun_out/sweep.jsonl", "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")
@@ -112,6 +143,8 @@ def main():
     print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
     for r in rows:
         g = lambda k, f="%.0f": (f % r[k]) if k in r and r[k] is not None else "-"   # noqa: E731
+        if r.get("kind") == "decoder":
+            r = dict(r, tokens=f"{r['tokens']} (N={r['N']}, Lq={r['Lq']})")
         print(f"| {r['tokens']} | {r['P']} | {r['dtype']} | {g('fwd_us')} | {g('bwd_us')} | {g('fwdbwd_Mq_s', '%.1f')} | "
               f"{g('ref_cuda_fwd_us')} | {g('ref_cuda_bwd_us')} | {g('speedup_fwd', '%.1f')} | {g('speedup_bwd', '%.1f')} | "
               f"{g('max_err_vs_ref_cuda', '%.1e')} | {g('cpu_fwdbwd_ms_per_frame', '%.0f')} | {g('speedup_vs_cpu_fwdbwd', '%.0f')} |")
