@@ -888,16 +888,17 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
 //   3. a group of G lanes per touched pixel sums  weight * grad_output[query]  over its run and stores the row.
 // No atomics on floating-point data, no workspace; bit-identical from run to run.
 constexpr int kDirectMax = 2048;    // contributions (4 per sample) of one (frame, head, level) held in shared memory
+constexpr int kDirectRows = 4096;   // grad_output elements of one (frame, head) staged in shared memory (fp32)
 
 template <typename T, typename TA, int VEC, int G>
 __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const Params p, const int K, const int id_bits) {
     constexpr int NG = kThreads / G;
-    constexpr int B = 4;                                  // grad_output rows in flight per lane
+    constexpr int D = VEC * G;
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
-    __shared__ uint32_t s_key[kDirectMax];
-    __shared__ float s_w[kDirectMax];
+    __shared__ unsigned long long s_kw[kDirectMax];       // key << 32 | weight bits: one 64-bit compare-exchange
     __shared__ uint16_t s_head[kDirectMax];               // first contribution of every touched pixel
+    __shared__ __align__(16) float s_g[kDirectRows];      // this (frame, head)'s grad_output rows, fp32
     __shared__ int s_nhead;
     load_levels(p, lv, &s_sb, &s_sq);
     const TA* __restrict__ loc = static_cast<const TA*>(p.loc);
@@ -908,13 +909,26 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
     const int nsamp = p.Lq * p.P;                         // samples of one (frame, head, level)
     const int pshift = id_bits + 2;
     const uint32_t idmask = (1u << id_bits) - 1u;
+    const bool staged = p.Lq * D <= kDirectRows;          // else the rows are read from global memory (L2)
     const int items = p.N * p.M * p.L;
+    int nm_staged = -1;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int l = it % p.L;
         const int nm = it / p.L;
         const int m = nm % p.M, n = nm / p.M;
         const Level L_ = lv[l];
+        const T* __restrict__ gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D;
+        const size_t qstride = (size_t)p.M * p.D;
         if (threadIdx.x == 0) s_nhead = 0;
+        if (staged && nm != nm_staged) {                  // consecutive items are the levels of one (frame, head)
+            for (int i = grp; i < p.Lq; i += NG) {
+                float g[VEC];
+                load_row<T, VEC>(gbase + (size_t)i * qstride + gl * VEC, g);
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) s_g[i * D + gl * VEC + c] = g[c];
+            }
+            nm_staged = nm;
+        }
         // 1. contributions
         for (int i = threadIdx.x; i < K / 4; i += kThreads) {
             uint32_t key[4] = {~0u, ~0u, ~0u, ~0u};
@@ -940,61 +954,60 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                s_key[4 * i + c] = key[c];
-                s_w[4 * i + c] = w[c];
+            for (int c = 0; c < 4; ++c)
+                s_kw[4 * i + c] = ((unsigned long long)key[c] << 32) | (unsigned long long)__float_as_uint(w[c]);
+        }
+        __syncthreads();
+        // 2. bitonic sort by key (keys are unique, so the weight bits below them never decide).  One thread per
+        //    compare-exchange, the same pairs of the same 64-element segments for a warp in every round at
+        //    distance <= 32, so between two such rounds a warp barrier is enough.
+        for (int k = 2; k <= K; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int pi = threadIdx.x; pi < K / 2; pi += kThreads) {
+                    const int t = 2 * pi - (pi & (j - 1)), u = t + j;
+                    const unsigned long long a0 = s_kw[t], a1 = s_kw[u];
+                    if ((a0 > a1) == ((t & k) == 0)) {
+                        s_kw[t] = a1;
+                        s_kw[u] = a0;
+                    }
+                }
+                // the next round exchanges at distance j/2 (or k, when this k is done): a block barrier unless
+                // both this round's writes and the next round's reads stay inside the warps' own segments
+                const int jn = j > 1 ? (j >> 1) : k;
+                if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
             }
         }
         __syncthreads();
-        // 2. bitonic sort by key, the weight rides along
-        for (int k = 2; k <= K; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = threadIdx.x; t < K; t += kThreads) {
-                    const int u = t ^ j;
-                    if (u > t) {
-                        const uint32_t a0 = s_key[t], a1 = s_key[u];
-                        if ((a0 > a1) == ((t & k) == 0)) {
-                            s_key[t] = a1; s_key[u] = a0;
-                            const float w0 = s_w[t];
-                            s_w[t] = s_w[u]; s_w[u] = w0;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
         // 3. runs of equal pixel (which group takes which run does not matter: runs are independent)
         for (int t = threadIdx.x; t < K; t += kThreads) {
-            const uint32_t kt = s_key[t];
-            if (kt != ~0u && (t == 0 || (s_key[t - 1] >> pshift) != (kt >> pshift)))
+            const uint32_t kt = (uint32_t)(s_kw[t] >> 32);
+            if (kt != ~0u && (t == 0 || ((uint32_t)(s_kw[t - 1] >> 32) >> pshift) != (kt >> pshift)))
                 s_head[atomicAdd(&s_nhead, 1)] = (uint16_t)t;
         }
         __syncthreads();
         const int nhead = s_nhead;
-        const T* __restrict__ gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
-        const size_t qstride = (size_t)p.M * p.D;
         for (int r = grp; r < nhead; r += NG) {
             int t = s_head[r];
-            const uint32_t pix = s_key[t] >> pshift;
+            const uint32_t pix = (uint32_t)(s_kw[t] >> 32) >> pshift;
             float acc[VEC];
 #pragma unroll
             for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-            while (t < K && (s_key[t] >> pshift) == pix) {
-                float g[B][VEC], w[B];
+            while (t < K) {
+                const unsigned long long kw = s_kw[t];
+                const uint32_t kt = (uint32_t)(kw >> 32);
+                if ((kt >> pshift) != pix) break;
+                const float w = __uint_as_float((uint32_t)kw);
+                const int q = (int)((kt >> 2) & idmask) / p.P;
+                float g[VEC];
+                if (staged) {
 #pragma unroll
-                for (int j = 0; j < B; ++j) {
-                    const bool on = t + j < K && (s_key[t + j] >> pshift) == pix;
-                    w[j] = on ? s_w[t + j] : 0.f;
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) g[j][c] = 0.f;
-                    if (on) load_row<T, VEC>(gbase + (size_t)(((s_key[t + j] >> 2) & idmask) / p.P) * qstride, g[j]);
+                    for (int c = 0; c < VEC; ++c) g[c] = s_g[q * D + gl * VEC + c];
+                } else {
+                    load_row<T, VEC>(gbase + (size_t)q * qstride + gl * VEC, g);
                 }
-                // contributions past the run's end carry weight 0 and a zero row: adding +0 changes nothing
 #pragma unroll
-                for (int j = 0; j < B; ++j)
-#pragma unroll
-                    for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[j], g[j][c], acc[c]);
-                t += B;
+                for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w, g[c], acc[c]);
+                ++t;
             }
             store_row<T, VEC>(gval + (((size_t)n * p.S + L_.start + pix) * p.M + m) * p.D + gl * VEC, acc);
         }

@@ -512,6 +512,23 @@ def test_grad_value_gathers_agree(kw, vdt, adt):
     assert _lib.load().msda_index_bytes(N, S, M, D, L, 600, P) > 0
 
 
+@pytest.mark.parametrize("N,Lq", [(16, 20), (36, 5), (36, 20), (16, 128)])
+def test_direct_gather_at_decoder_batch_sizes(N, Lq):
+    """The SOC decoder calls (A2D: 16 frames x 20 queries; Ref-YouTube-VOS: 36 frames x 5 / 20 queries) with every
+    SM busy: the direct gather against the index pipeline (different summation order, so to tolerance) and
+    against itself (bit for bit, 3 runs)."""
+    x = make_inputs(N=N, Lq=Lq, dist="decoder", seed=29)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    dense = run_op(*a, torch.float32, torch.float32, flags=_lib.FLAG_WALK_DENSE)
+    runs = [run_op(*a, torch.float32, torch.float32) for _ in range(3)]
+    assert rel_err(runs[0][1], dense[1].double().cpu().numpy()) <= 1e-5
+    assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][1], runs[2][1])
+    x1 = make_inputs(N=1, Lq=Lq, dist="decoder", seed=29)
+    v, lo, at, go = (t[:1] for t in dense[4])
+    r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
+    assert rel_err(runs[0][1][:1], r_gv) <= 1e-5
+
+
 def test_direct_gather_is_frame_independent():
     """The gather is chosen from per-frame quantities only: a frame's gradients do not depend on its batch."""
     x = make_inputs(N=4, dist="decoder", Lq=20, seed=23)
