@@ -16,7 +16,9 @@ ap.add_argument("--lq", type=int, default=0, help="queries per frame (decoder di
 ap.add_argument("--dtype", default="bf16mix")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--self-count", action="store_true", help="backward without the forward's index")
+ap.add_argument("--flags", type=int, default=0, help="MSDA_FLAG_* bits for every call (A/B switches)")
 a = ap.parse_args()
+msda_ext.DEFAULT_FLAGS = a.flags
 vdt, adt = {"fp32": (torch.float32, torch.float32), "bf16mix": (torch.bfloat16, torch.float32),
             "bf16": (torch.bfloat16, torch.bfloat16)}[a.dtype]
 x = (make_inputs(N=a.N, Lq=a.lq, dist="decoder", seed=0) if a.lq else make_inputs(N=a.N, dist="encoder", seed=0))
