@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["MSDA_LIB"]) if os.environ.get("MSDA_LIB") else PKG / "libmsda_b200.so"
 
 F32, BF16, F16, F64 = 0, 1, 2, 3
-FLAG_PYRAMID_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC8 = 1, 2, 4, 8
+FLAG_PYRAMID_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC4 = 1, 2, 4, 8
 FLAG_WALK_DENSE = 16
 
 EXPORTS = (

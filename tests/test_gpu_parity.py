@@ -443,14 +443,14 @@ def test_module_fused_prologue_matches_unfused(amp):
 
 
 def test_bf16_lane_layout_switch():
-    """MSDA_FLAG_BF16_VEC8 (64-byte bf16 rows on 4 lanes x 128 bit instead of 8 lanes x 64 bit) is an A/B
+    """MSDA_FLAG_BF16_VEC4 (64-byte bf16 rows on 8 lanes x 64 bit instead of 4 lanes x 128 bit) is an A/B
     switch: same arithmetic per row, so results agree to the last bit in the forward and to bf16 rounding in
     the backward (the cross-lane reduction tree differs)."""
     x = make_inputs(N=2, dist="encoder", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], seed=81)
     a = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
                x.grad_output, torch.bfloat16, torch.float32)
     b = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights,
-               x.grad_output, torch.bfloat16, torch.float32, flags=_lib.FLAG_BF16_VEC8)
+               x.grad_output, torch.bfloat16, torch.float32, flags=_lib.FLAG_BF16_VEC4)
     assert torch.equal(a[0], b[0])
     for i in (1, 2, 3):
         assert rel_err(a[i], b[i].double().cpu().numpy()) <= 2e-2

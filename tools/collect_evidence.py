@@ -67,9 +67,9 @@ if traffic:
 lib = ROOT / "neurips2023_soc_b200" / "libmsda_b200.so"
 names = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True).stdout
 want = {
-    "fwd_tile_bf16": "msda_fwd_tile_kernelI13__nv_bfloat16fLi4ELi8ELi4ELb1ELb0ELi512E",
+    "fwd_tile_bf16": "msda_fwd_tile_kernelI13__nv_bfloat16fLi8ELi4ELi4ELb1ELb0ELi512E",
     "fwd_tile_f32": "msda_fwd_tile_kernelIffLi4ELi8ELi4ELb1ELb0ELi1024E",
-    "bwd_sample_tile_bf16": "msda_bwd_sample_tile_kernelI13__nv_bfloat16fLi4ELi8ELi4ELb1ELb0ELi512E",
+    "bwd_sample_tile_bf16": "msda_bwd_sample_tile_kernelI13__nv_bfloat16fLi8ELi4ELi4ELb1ELb0ELi512E",
     "grad_value_walk_bf16": "msda_grad_value_walk_kernelI13__nv_bfloat16Li4ELi8E",
     "bin_rank_sort_f32": "msda_bin_rank_sort_kernelIfE",
     "grad_value_direct_f32": "msda_grad_value_direct_kernelIffLi4ELi8E",
