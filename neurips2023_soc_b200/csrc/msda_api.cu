@@ -8,6 +8,7 @@
 // the caller's stream.  Unlike the reference (cuh:948-952) launch errors are returned.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -331,13 +332,31 @@ int launch_sort(const Params& p, cudaStream_t st) {
     return MSDA_OK;
 }
 
+// Dense-level tile of the walker.  A dense tile is one CTA's serial work (thousands of entries, ~150 us for a
+// 12 x 8 tile of the coarsest A2D level): with many (frame, head) pairs the big tile wins (least halo re-walk),
+// with few the launch is as long as one tile, so the tiles shrink until there are enough of them.
+// MSDA_WALK_DENSE_TILE="HxW" overrides (tuning).
+void walk_dense_tile(const Params& p, int& thd, int& twd) {
+    thd = MSDA_WALK_THD; twd = MSDA_WALK_TWD;
+    const long long nm = (long long)p.N * p.M;
+    // measured on B200, A2D pyramid, walker us at N = 2 / 8 / 16 frames x 8 heads:
+    //   12x8: 148 / 184 / 282    12x4: 100 / 144 / 290    6x4: 99 / 148 / 295    3x4: 65 / 152 / 308    2x2: 65 / 186 / 373
+    if (nm < 96) { thd = 12; twd = 4; }
+    if (nm < 48) { thd = 6; twd = 4; }
+    if (nm < 24) { thd = 3; twd = 4; }
+    static const char* env = getenv("MSDA_WALK_DENSE_TILE");
+    if (env) { int a = 0, b = 0; if (sscanf(env, "%dx%d", &a, &b) == 2 && a > 0 && b > 0) { thd = a; twd = b; } }
+}
+
 template <typename T, int VEC, int G>
 int launch_grad_value_walk(const Params& p, cudaStream_t st) {
     auto k = msda_grad_value_walk_kernel<T, VEC, G>;
+    int thd, twd;
+    walk_dense_tile(p, thd, twd);
     // tiles per (frame, head) are only known on the device; S / 8 bounds them from above
     const long long tiles = (long long)p.N * p.M * (p.S / 8 + p.L);
     prof_begin(st, "msda_grad_value_walk_kernel");
-    k<<<persistent_grid(k, kGThreads, tiles), kGThreads, 0, st>>>(p);
+    k<<<persistent_grid(k, kGThreads, tiles), kGThreads, 0, st>>>(p, thd, twd);
     prof_end(st);
     MSDA_LAUNCHED("msda_grad_value_walk_kernel");
     return MSDA_OK;

@@ -658,7 +658,7 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
 #endif
 
 template <typename T, int VEC, int G>
-__global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_value_walk_kernel(const Params p) {
+__global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_value_walk_kernel(const Params p, const int thd, const int twd) {
     constexpr int D = VEC * G;
     constexpr int NGRP = kGThreads / G;          // groups per CTA
     constexpr int GW = 32 / G;                   // groups per warp
@@ -678,7 +678,9 @@ __global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_val
 #ifndef MSDA_WALK_TWD
 #define MSDA_WALK_TWD 8
 #endif
-    constexpr int TH_D = (MSDA_WALK_THD) < TH ? (MSDA_WALK_THD) : TH, TW_D = MSDA_WALK_TWD;
+    // thd x twd: the dense-level tile, chosen per launch (api: walk_dense_tile) -- it changes how the bins are
+    // spread over CTAs, never the order in which a bin's entries or a pixel's four bins are summed
+    const int TH_D = thd < TH ? thd : TH, TW_D = twd < TW ? twd : TW;
 
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
