@@ -396,8 +396,12 @@ int launch_grad_value_generic(const Params& p, cudaStream_t st) {
 }
 
 // ---- (dtype, VEC, G, P) dispatch tables ------------------------------------------------------
+#ifdef MSDA_SLIM   // variant builds for A/B runs (tools/build_variant.sh): D = 32, P = 4 only
+#define MSDA_FOR_P(CALL, T, TA, VEC, G) (((VEC) * (G) == 32 && p.P == 4) ? CALL<T, TA, (VEC) * (G) == 32 ? (VEC) : 4, (VEC) * (G) == 32 ? (G) : 8, 4>(p, st) : fail(MSDA_ERR_UNSUPPORTED, "slim build"))
+#else
 #define MSDA_FOR_P(CALL, T, TA, VEC, G)                         \
     (p.P == 4 ? CALL<T, TA, VEC, G, 4>(p, st) : CALL<T, TA, VEC, G, 8>(p, st))
+#endif
 
 template <typename TA>
 int dispatch_fwd_tile(const Params& p, const Plan& pl, int vdt, cudaStream_t st) {

@@ -36,7 +36,8 @@ namespace msda {
 // FUSED: the softmax / sampling-location prologue of MSDeformAttn.forward runs in the staging
 // threads (TA is then the dtype of the raw offsets / logits; the results are fp32).
 template <typename T, typename TA, int VEC, int G, int P, bool COUNT, bool FUSED = false, int ROWB = 0>
-__global__ void __launch_bounds__(kThreads, MSDA_FWD_MIN_BLOCKS) msda_fwd_tile_kernel(const Params p, const int rounds) {
+__global__ void __launch_bounds__(kThreads, (VEC == 8 && G == 4) ? 3 : MSDA_FWD_MIN_BLOCKS)   // 4 wide lanes per row: 80 registers, no spill (222 -> 212 us)
+msda_fwd_tile_kernel(const Params p, const int rounds) {
     constexpr int MODE = COUNT ? kIndexCount : kIndexNone;
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
