@@ -39,13 +39,15 @@ if log.exists():
 
 # ncu --set full summaries
 traffic = {}
-for rep, name in (("full_bf16mix.ncu-rep", f"{TAG}_ncu_full_bf16mix_summary.txt"),
-                  ("full_direct.ncu-rep", f"{TAG}_ncu_full_direct_gather_summary.txt")):
-    if not (OUT / rep).exists():
+for rep, name in (("full_bf16mix", f"{TAG}_ncu_full_bf16mix_summary.txt"),
+                  ("full_direct", f"{TAG}_ncu_full_direct_gather_summary.txt")):
+    tmp = OUT / (rep + ".raw.csv")          # exported on the GPU box (the reports exceed gpurun's 64 MiB return)
+    if not tmp.exists() and (OUT / (rep + ".ncu-rep")).exists():
+        tmp.write_text(subprocess.run(["ncu", "-i", str(OUT / (rep + ".ncu-rep")), "--page", "raw", "--csv"],
+                                      capture_output=True, text=True).stdout)
+    if not tmp.exists():
         continue
-    raw = subprocess.run(["ncu", "-i", str(OUT / rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    tmp = OUT / (rep + ".raw.csv")
-    tmp.write_text(raw)
+    raw = tmp.read_text()
     txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(tmp)], capture_output=True, text=True).stdout
     (PROF / name).write_text(txt)
     print("wrote", name)

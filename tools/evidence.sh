@@ -16,6 +16,11 @@ for dt in fp32 bf16mix; do
 done
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"msda_(fwd_tile|bwd_sample_tile|bin_rank_sort|grad_value_walk)" -s 8 -c 4 -o gpurun_out/full_bf16mix python tools/one_step.py --dtype bf16mix --steps 3 > gpurun_out/ncu_full.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"msda_grad_value_direct" -c 1 -o gpurun_out/full_direct python tools/kernel_times.py --lq 20 --dtype fp32 --steps 1 > /dev/null 2>&1
+# gpurun brings back at most 64 MiB: keep the raw-metric pages, not the reports
+for r in full_bf16mix full_direct; do
+  ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/$r.raw.csv 2>/dev/null
+  rm -f gpurun_out/$r.ncu-rep
+done
 timeout 400 python tools/probe.py --iters 15 --dists encoder,uniform > gpurun_out/probe_n16.log 2>&1; cp gpurun_out/probe.json gpurun_out/probe_n16.json
 timeout 200 python tools/probe.py --iters 15 --dists encoder --N 2 > gpurun_out/probe_n2.log 2>&1; cp gpurun_out/probe.json gpurun_out/probe_n2.json
 timeout 600 python tools/sweep.py --decoder > gpurun_out/sweep.log 2>&1; tail -34 gpurun_out/sweep.log
