@@ -657,8 +657,15 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
 #define MSDA_WALK_MIN_BLOCKS 6
 #endif
 
+// CTAs per SM, measured on B200 at the A2D shape (D = 32): bf16 rows 5 / 6 / 7 / 8 -> 283 / 283 / 263 / 278 us,
+// fp32 rows 5 / 6 / 7 -> 321 / 333 / 360 us (the kernel is latency-bound; registers vs. rows in flight)
 template <typename T, int VEC, int G>
-__global__ void __launch_bounds__(kGThreads, MSDA_WALK_MIN_BLOCKS) msda_grad_value_walk_kernel(const Params p, const int thd, const int twd) {
+constexpr int walk_min_blocks() {
+    return (G == 8 && VEC == 4) ? (sizeof(T) == 2 ? 7 : 5) : MSDA_WALK_MIN_BLOCKS;
+}
+
+template <typename T, int VEC, int G>
+__global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_grad_value_walk_kernel(const Params p, const int thd, const int twd) {
     constexpr int D = VEC * G;
     constexpr int NGRP = kGThreads / G;          // groups per CTA
     constexpr int GW = 32 / G;                   // groups per warp
