@@ -138,10 +138,22 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
     const int sg = w.c0 + st_s;
     const int l = min(sg / P, p.L - 1);
     const Level L_ = lv[l];
+    const size_t nm = (size_t)tl.n * p.M + tl.m;
+    const bool fill = MODE == kIndexFill && p.entries != nullptr;   // null: the direct gather follows, no index is kept
+    // With 4 descriptors per thread (4-lane rows) the slot atomics of a thread are issued together and the entries
+    // written in a second pass: waiting for each atomic's return in turn was 23 % of the sample-gradient kernel's
+    // stall samples (300 -> 288 us).  With 2 per thread (8-lane rows) the extra live registers cost more (fp32
+    // 394 -> 405 us), so those store at once.
+    constexpr bool TWO_PASS = MODE == kIndexFill && DPT >= 4;
+    uint4 dsc[DPT];
+    uint32_t slot[DPT];
+    bool live[DPT];
+    // pass 1: descriptors, and every accepted sample's integer atomic (count, or take a slot)
 #pragma unroll
     for (int k = 0; k < DPT; ++k) {
-        const int j = st_j0 + k * (kThreads / kSC);
         uint4 d = make_uint4(0u, 0u, 0u, 0u);
+        live[k] = false;
+        slot[k] = 0u;
         if (st.q[k] >= 0) {
             const Sample<float> s = locate(st.x[k], st.y[k], L_.H, L_.W);
             if (s.ok) {
@@ -153,22 +165,37 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
                 d.z = __float_as_uint(s.lw);
                 d.w = __float_as_uint(st.a[k]);
                 if constexpr (MODE != kIndexNone) {
-                    const size_t nm = (size_t)tl.n * p.M + tl.m;
                     // slot b+1 of the table row belongs to sub-bin b (see msda_bin_scan_kernel)
                     const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]) + 1;
                     if constexpr (MODE == kIndexCount) {
                         atomicAdd(p.bin_off + b, 1u);
-                    } else if (p.entries != nullptr) {   // null: the direct gather follows, no index is kept
-                        const uint32_t slot = atomicAdd(p.bin_off + b, 1u);
-                        uint4 e;
-                        e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;
-                        e.y = d.y; e.z = d.z; e.w = d.w;
-                        static_cast<uint4*>(p.entries)[nm * ((size_t)p.Lq * p.LP) + slot] = e;
+                    } else if (fill) {
+                        slot[k] = atomicAdd(p.bin_off + b, 1u);
+                        live[k] = true;
+                        if constexpr (!TWO_PASS) {
+                            uint4 e;
+                            e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;
+                            e.y = d.y; e.z = d.z; e.w = d.w;
+                            static_cast<uint4*>(p.entries)[nm * ((size_t)p.Lq * p.LP) + slot[k]] = e;
+                        }
                     }
                 }
             }
         }
-        desc[j * kDescStride + st_s] = d;
+        dsc[k] = d;
+        desc[(st_j0 + k * (kThreads / kSC)) * kDescStride + st_s] = d;
+    }
+    // pass 2: the index entries go to the slots taken above
+    if constexpr (TWO_PASS) {
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            if (live[k]) {
+                uint4 e;
+                e.x = ((uint32_t)st.q[k] << p.id_shift) | (uint32_t)sg;
+                e.y = dsc[k].y; e.z = dsc[k].z; e.w = dsc[k].w;
+                static_cast<uint4*>(p.entries)[nm * ((size_t)p.Lq * p.LP) + slot[k]] = e;
+            }
+        }
     }
 }
 
