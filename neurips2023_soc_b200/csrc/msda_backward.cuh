@@ -414,23 +414,21 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
     const int nm = blockIdx.x;
     uint32_t* data = p.bin_off + (size_t)nm * (p.sb_max + 1) + 1;
     const int SB = s_sb;
-    const int ipt = (SB + blockDim.x - 1) / blockDim.x;
-    const int beg = min(SB, (int)threadIdx.x * ipt), end = min(SB, beg + ipt);
-    uint32_t sum = 0;
-    for (int i = beg; i < end; ++i) {
-        sum += data[i];
-    }
+    // every warp owns one contiguous segment and walks it 32 counts at a time (coalesced), twice: totals first,
+    // then the exclusive offsets on top of the scanned warp totals
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t inc = sum;
+    const int seg = (((SB + 31) / 32) + 31) & ~31;          // per-warp segment, a multiple of 32
+    const int beg = min(SB, wid * seg), end = min(SB, beg + seg);
+    uint32_t sum = 0;
+#pragma unroll 4
+    for (int i = beg + lane; i < end; i += 32) sum += data[i];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) warp_tot[wid] = inc;
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) warp_tot[wid] = sum;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = warp_tot[lane], wi = w;
+        const uint32_t w = warp_tot[lane];
+        uint32_t wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
@@ -439,12 +437,20 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
         warp_tot[lane] = wi - w;  // exclusive
     }
     __syncthreads();
-    uint32_t run = warp_tot[wid] + inc - sum;
-    for (int i = beg; i < end; ++i) {
-        const uint32_t c = data[i];
-        data[i] = run;
-        run += c;
+    uint32_t run = warp_tot[wid];
+    for (int i0 = beg; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t c = i < end ? data[i] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (i < end) data[i] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
+}
 }
 
 template <typename TA, typename CT>
