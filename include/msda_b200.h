@@ -141,6 +141,20 @@ int msda_forward_fused(const void *value, const int64_t *spatial_shapes, const i
                        int N, int S, int M, int D, int L, int Lq, int P,
                        int value_dtype, int in_dtype, int im2col_step, void *cuda_stream, unsigned flags);
 
+/* Backward of msda_forward_fused: like msda_backward_indexed on the saved sampling_loc / attn_weight (the fp32
+ * tensors the fused forward wrote), but the chain rule of the prologue is applied on the way out --
+ *   grad_sampling_offsets = grad_sampling_loc / (W_l, H_l)
+ *   grad_attn_logits      = attn_weight * (grad_attn_weight - sum_over_L*P(attn_weight * grad_attn_weight))
+ * written in aux_dtype with the layouts of sampling_loc / attn_weight.  (The gradient of the reference points, when
+ * needed, is the sum of grad_sampling_offsets * (W_l, H_l) over heads and points.)  Same shape support as
+ * msda_forward_fused; anything else returns MSDA_ERR_UNSUPPORTED. */
+int msda_backward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                        void *grad_value, void *grad_sampling_offsets, void *grad_attn_logits,
+                        void *workspace, size_t workspace_bytes, void *index, size_t index_bytes,
+                        int N, int S, int M, int D, int L, int Lq, int P,
+                        int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
+
 /* Bytes of device scratch msda_backward needs for this problem size. */
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P,
                                      int value_dtype, int aux_dtype);

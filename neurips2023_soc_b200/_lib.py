@@ -19,7 +19,7 @@ EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",
     "msda_backward_workspace_bytes", "msda_backward", "msda_backward_ex", "msda_last_launch_count",
     "msda_profile_enable", "msda_profile_read",
-    "msda_index_bytes", "msda_forward_indexed", "msda_backward_indexed", "msda_forward_fused",
+    "msda_index_bytes", "msda_forward_indexed", "msda_backward_indexed", "msda_forward_fused", "msda_backward_fused",
 )
 
 _lib = None
@@ -61,6 +61,8 @@ def load() -> ctypes.CDLL:
     lib.msda_forward_fused.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp, u]
     lib.msda_backward_indexed.restype = i
     lib.msda_backward_indexed.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
+    lib.msda_backward_fused.restype = i
+    lib.msda_backward_fused.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     lib.msda_profile_enable.restype = None
     lib.msda_profile_enable.argtypes = [i]
     lib.msda_profile_read.restype = i

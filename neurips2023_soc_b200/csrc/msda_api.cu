@@ -239,6 +239,8 @@ int launch_fwd_generic(const Params& p, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // backward
+constexpr unsigned kFlagChain = 0x80000000u;   // internal: msda_backward_fused (never set through the public flags)
+
 template <typename T, typename TA, int VEC, int G, int P, int ROWB>
 int launch_bwd_sample_tile_rowb(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
@@ -253,6 +255,14 @@ int launch_bwd_sample_tile_rowb(const Params& p, cudaStream_t st) {
             MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<atomic>");
             return MSDA_OK;
         }
+    }
+    if (p.flags & kFlagChain) {
+        auto kc = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false, ROWB, true>;
+        prof_begin(st, "msda_bwd_sample_tile_kernel<chain>");
+        kc<<<persistent_grid(kc, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+        prof_end(st);
+        MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<chain>");
+        return MSDA_OK;
     }
     auto k = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false, ROWB>;   // FILL: writes the index entries
     prof_begin(st, "msda_bwd_sample_tile_kernel");
@@ -727,13 +737,14 @@ size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, 
     return ws_layout(N, S, M, L, Lq, P, value_dtype).total;
 }
 
-int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                          const void* sampling_loc, const void* attn_weight, const void* grad_output,
-                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
-                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
-                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
-                          unsigned flags) {
+static int backward_impl(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                         void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                         size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
+                         int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
+                         unsigned flags, bool chain) {
     g_launches = 0;
+    flags &= ~kFlagChain;
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
     if (rc) return rc;
@@ -783,6 +794,13 @@ int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, cons
                      aligned16(attn_weight) && aligned16(grad_sampling_loc) && aligned16(grad_attn_weight)))
         pl.tile = false;
     if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;
+    if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 31)) pl.tile = false;  // signed 32-bit byte offsets
+    if (chain) {
+        if (!(pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16)) || LP > kSC ||
+            (flags & (MSDA_FLAG_ATOMIC_GRAD_VALUE | MSDA_FLAG_GENERIC)))
+            return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue exists for the tile kernels only (fp32/bf16, D and P as in DESIGN.md, L*P <= %d)", kSC);
+        p.flags |= kFlagChain;
+    }
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {
@@ -795,6 +813,28 @@ int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, cons
                          : backward_typed<__half, __half, float>(p, pl, value_dtype, index, table_bytes, st);
         default: return backward_typed<double, double, double>(p, pl, value_dtype, index, table_bytes, st);
     }
+}
+
+int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
+                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
+                          unsigned flags) {
+    return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
+                         grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes, index, index_size, N, S, M, D,
+                         L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags, false);
+}
+
+int msda_backward_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                        const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                        void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* workspace,
+                        size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
+                        int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
+                        unsigned flags) {
+    return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
+                         grad_sampling_offsets, grad_attn_logits, workspace, workspace_bytes, index, index_size, N, S, M,
+                         D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags, true);
 }
 
 int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

@@ -88,7 +88,11 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
 // part B (one integer atomic + one 16-byte store, overlapped with the gather).  ATOMIC:
 // bench-only A/B arm that scatters grad_value with 128-bit fp32 reductions like the reference
 // does with scalar ones.
-template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC, int ROWB = 0>
+// CHAIN: the chain rule of the module's prologue (/root/reference/models/ops/modules/ms_deform_attn.py:99-106) is
+// applied on the way out: grad_loc / grad_attn then hold the gradients of the RAW sampling offsets and attention
+// logits --  d/d offset = grad_loc / (W, H) = a * (dX, dY);  d/d logit_s = a_s * (g_s - sum_t a_t g_t)  (softmax) --
+// for calls whose L*P samples are one chunk (the fused prologue's own restriction).
+template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC, int ROWB = 0, bool CHAIN = false>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         constexpr int LPS = CPL >= 4 ? 1 : 4 / CPL;  // lanes that share one sample afterwards
         constexpr int SPL = CPL >= 4 ? CPL / 4 : 1;  // samples per lane afterwards
         static_assert(NV % G == 0 && (CPL >= 4 ? CPL % 4 == 0 : 4 % CPL == 0), "unsupported G / P combination");
+        float chain_dot = 0.f;                       // CHAIN: this lane's share of sum_t a_t g_t
 #pragma unroll 1
         for (int lc = 0; lc < LPC; ++lc) {
             const int l = l0 + lc;
@@ -284,7 +289,36 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
                     const size_t si = qm_mine * p.LP + sgo;
                     gattn[si] = Elem<TA>::from_f(ga);
-                    store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
+                    if constexpr (CHAIN) {
+                        store_xy(gloc + 2 * si, a * gx, a * gy);
+                        chain_dot = fmaf(a, ga, chain_dot);
+                    } else {
+                        store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
+                    }
+                }
+            }
+        }
+        if constexpr (CHAIN) {
+            // softmax backward: the lanes that wrote a sample's d/d weight come back to it once the (query, head)'s
+            // sum is known (their own stores, re-read in program order)
+            const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+#pragma unroll
+            for (int dd = 1; dd < G; dd <<= 1) chain_dot += __shfl_xor_sync(gmask, chain_dot, dd, G);
+#pragma unroll 1
+            for (int lc = 0; lc < LPC; ++lc) {
+                if (l0 + lc >= p.L) break;
+                const int sbase = (P >= kSC) ? 0 : lc * PPC;
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const int s = (gl * CPL) / 4 + i;
+                    const int sgo = cur.c0 + sbase + s;
+                    if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
+                        const size_t si = qm_mine * p.LP + sgo;
+                        // the weight comes from the tensor, not the descriptor: a rejected sample's descriptor is all
+                        // zero, yet its logit still takes  -a_s * sum_t a_t g_t
+                        const float a = (float)Elem<TA>::to_f(attn[si]);
+                        gattn[si] = Elem<TA>::from_f(a * ((float)Elem<TA>::to_f(gattn[si]) - chain_dot));
+                    }
                 }
             }
         }
@@ -450,7 +484,6 @@ __global__ void __launch_bounds__(1024) msda_bin_scan_kernel(const Params p) {
         if (i < end) data[i] = run + inc - c;
         run += __shfl_sync(0xffffffffu, inc, 31);
     }
-}
 }
 
 template <typename TA, typename CT>

@@ -70,7 +70,8 @@ class MSDeformAttnFusedFunction(Function):
     The forward kernel forms ``softmax(attention_logits)`` and ``reference_points + sampling_offsets / (W, H)``
     in its staging threads (one pass over the raw projections instead of five elementwise kernels) and writes
     both out in fp32, as autocast would produce them.  The backward runs the same kernels as
-    ``MSDeformAttnFunction`` on those saved tensors and applies the chain rule of the two elementwise maps.
+    ``MSDeformAttnFunction`` on those saved tensors; the chain rule of the two elementwise maps is applied inside the
+    sample-gradient kernel (msda_backward_fused) unless someone differentiated through the returned tensors.
     Only for shapes ``msda_ext.fused_prologue_supported`` accepts.
     """
 
@@ -96,9 +97,21 @@ class MSDeformAttnFusedFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output, grad_loc_out, grad_attn_out):
         value, shapes, lsi, loc, attn = ctx.saved_tensors
+        go = grad_output.to(value.dtype).contiguous()
+        index, ctx.index = ctx.index, None
+        if grad_loc_out is None and grad_attn_out is None:
+            # nobody differentiated through the returned locations / weights (the encoder drops them, the decoder
+            # only ranks them): the chain rule of softmax and of ref + off / (W, H) runs inside the kernel
+            grad_value, grad_offsets, grad_logits = msda_ext.ms_deform_attn_backward_fused(
+                value, shapes, lsi, loc, attn, go, ctx.im2col_step, index=index)
+            grad_ref = None
+            if ctx.needs_input_grad[3]:
+                wh = shapes.flip(-1).to(grad_offsets.dtype)[None, None, None, :, None, :]
+                grad_ref = (grad_offsets * wh).sum(dim=(2, 4)).to(ctx.in_dtypes[2])
+            return (grad_value, None, None, grad_ref, grad_offsets.to(ctx.in_dtypes[0]),
+                    grad_logits.flatten(-2).to(ctx.in_dtypes[1]), None)
         grad_value, grad_loc, grad_attn = msda_ext.ms_deform_attn_backward(
-            value, shapes, lsi, loc, attn, grad_output.to(value.dtype).contiguous(), ctx.im2col_step, index=ctx.index)
-        ctx.index = None
+            value, shapes, lsi, loc, attn, go, ctx.im2col_step, index=index)
         if grad_loc_out is not None:          # someone differentiated through the returned locations / weights
             grad_loc = grad_loc + grad_loc_out
         if grad_attn_out is not None:

@@ -165,6 +165,34 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
+def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                  im2col_step: int, flags: int | None = None, index=None) -> List[torch.Tensor]:
+    """Backward of ``ms_deform_attn_forward_fused`` (msda_backward_fused): takes the saved fp32 sampling locations /
+    attention weights and returns ``[grad_value, grad_sampling_offsets, grad_attention_logits]`` -- the chain rule
+    of the module's softmax and location arithmetic is applied inside the sample-gradient kernel."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), ("grad_output", grad_output)])
+    dims, vdt, adt = _problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    N, S, M, D, L, Lq, P = dims
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == N * Lq * M * D,
+             "grad_output must be (N, Lq, M*D) in the dtype of value")
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty_like(sampling_loc)
+        grad_logits = torch.empty_like(attn_weight)
+        ws_bytes = int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+        _lib.check(lib.msda_backward_fused(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+            grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(),
+            ws.data_ptr(), ws_bytes, None if index is None else index.data_ptr(),
+            0 if index is None else index.numel(), *dims, vdt, adt, int(im2col_step),
+            torch.cuda.current_stream().cuda_stream, DEFAULT_FLAGS if flags is None else flags))
+    return [grad_value, grad_off, grad_logits]
+
+
 def fused_prologue_supported(value, n_levels: int, n_points: int, ref_dim: int) -> bool:
     """Whether ms_deform_attn_forward_fused has a kernel for this call: tile-kernel
     shapes (fp32 rows of 64/128/256 B, bf16 rows of 64/128/256 B, P in {4, 8}), L*P <= 16, 2-d reference

@@ -538,3 +538,38 @@ def test_direct_gather_is_frame_independent():
                  x.attention_weights[2:3], x.grad_output[2:3], torch.float32, torch.float32)
     for i in range(4):
         assert torch.equal(full[i][2:3], one[i])
+
+
+@pytest.mark.parametrize("vdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kw", [dict(N=2, dist="encoder", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)]),
+                                dict(N=2, dist="uniform", shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], Lq=300),
+                                dict(N=3, dist="decoder", Lq=20),
+                                dict(N=1, dist="uniform", shapes=[(9, 11), (4, 5)], M=3, D=64, Lq=70, P=8)])
+def test_backward_fused_applies_the_prologue_chain_rule(kw, vdt):
+    """msda_backward_fused against msda_backward_indexed followed by the chain rule of the module's prologue in
+    torch: grad_offsets = grad_loc / (W, H), grad_logits = softmax backward over the L*P weights of a (query,
+    head) -- including samples the op rejects (zero grad_attn, yet their logit takes -a * sum).  grad_value is
+    the same kernels' output: bit for bit."""
+    x = make_inputs(seed=53, **kw)
+    d = x.to(DEV, vdt, torch.float32)
+    a = (d.value, d.spatial_shapes, d.level_start_index, d.sampling_locations, d.attention_weights)
+    _, index = msda_ext.ms_deform_attn_forward(*a, 64, want_index=True)
+    gv, gl, ga = msda_ext.ms_deform_attn_backward(*a, d.grad_output, 64, index=index)
+    _, index = msda_ext.ms_deform_attn_forward(*a, 64, want_index=True)
+    fv, foff, flog = msda_ext.ms_deform_attn_backward_fused(*a, d.grad_output, 64, index=index)
+    wh = d.spatial_shapes.flip(-1).float()[None, None, None, :, None, :]
+    attn = d.attention_weights
+    want_off = gl / wh
+    want_log = attn * (ga - (ga * attn).sum(dim=(-1, -2), keepdim=True))
+    assert torch.equal(fv, gv)
+    scale = lambda t: max(1.0, float(t.abs().max()))   # noqa: E731
+    assert float((foff - want_off).abs().max()) <= 1e-5 * scale(want_off)
+    assert float((flog - want_log).abs().max()) <= 1e-5 * scale(want_log)
+    assert float(flog.abs().max()) > 0
+
+
+def test_backward_fused_rejects_what_it_has_no_kernel_for():
+    x = make_inputs(N=1, shapes=[(6, 7), (3, 4)], M=2, D=20, Lq=9, P=4, dist="uniform", seed=3).to(DEV)
+    with pytest.raises(RuntimeError, match="fused prologue"):
+        msda_ext.ms_deform_attn_backward_fused(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                               x.attention_weights, x.grad_output, 64)
