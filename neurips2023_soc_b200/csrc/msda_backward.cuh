@@ -520,12 +520,18 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
 // about six entries) and is written back to `first slot + rank`.  All lanes do the same amount
 // of work whatever the sub-bin sizes are.  Sub-bins with more than kRankMax entries go to the
 // big list instead (msda_bin_sort_big_kernel: bitonic network, one CTA per sub-bin).
-constexpr int kRankSpan = 128;   // sub-bins staged per step (at most)
+#ifndef MSDA_RANK_SPAN
+#define MSDA_RANK_SPAN 128
+#endif
+#ifndef MSDA_RANK_STAGE_BYTES
+#define MSDA_RANK_STAGE_BYTES 16384
+#endif
+constexpr int kRankSpan = MSDA_RANK_SPAN;   // sub-bins staged per step (at most)
 constexpr int kRankMax = 512;    // largest sub-bin ranked by counting
 
 template <typename CT>
 __global__ void __launch_bounds__(kThreads) msda_bin_rank_sort_kernel(const Params p) {
-    constexpr int CAP = 16384 / (int)sizeof(Entry<CT>);     // entries staged per step
+    constexpr int CAP = MSDA_RANK_STAGE_BYTES / (int)sizeof(Entry<CT>);     // entries staged per step
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     __shared__ Entry<CT> buf[CAP];
