@@ -10,7 +10,8 @@
 // bench's location distribution (descriptors precomputed, so that only the gather differs):
 //   A  [S][M][D], 4 lanes x 128 bit x 4 corners          (what msda_fwd_tile_kernel does today)
 //   B  [M][S][D], 4 lanes x 256 bit x 2 corner pairs      (lane = column x channel half; one shuffle-add at the end)
-//   T  the transpose that layout B needs once per call
+//   C  as B for the finest level, the three coarse levels of a (frame, head) staged in shared memory
+//   T  the transpose that layouts B / C need once per call
 // and checks that A and B agree.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/gather_probe tools/gather_probe.cu
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -25,6 +26,8 @@
 
 constexpr int M = 8, D = 32, L = 4, P = 4, LP = 16;
 constexpr int HS[L] = {48, 24, 12, 6}, WS[L] = {80, 40, 20, 10};
+__host__ __device__ constexpr int hs(int l) { return 48 >> l; }
+__host__ __device__ constexpr int ws(int l) { return 80 >> l; }
 constexpr int S = 5100, Lq = 5100;
 constexpr int kThreads = 256, kRows = kThreads / 4;      // (query, head) rows per CTA pass
 
@@ -148,6 +151,111 @@ __global__ void __launch_bounds__(kThreads, 3) gather_b(const __nv_bfloat16* __r
     }
 }
 
+// C: as B for level 0; levels 1..3 of the CTA's (frame, head) are staged once in shared memory with a zero border
+// (26x42 + 14x22 + 8x12 pixels x 64 B = 95,744 B), so that their corner pairs are plain shared-memory reads: no L1
+// tags, no L2 misses, no corner predicates.  A CTA of 512 threads (128 lane groups) takes one (frame, head, quarter of
+// the queries); two CTAs fit an SM.
+constexpr int kCThreads = 512, kCRanges = 4;
+constexpr int kPadBytes = (26 * 42 + 14 * 22 + 8 * 12) * 64;
+
+__global__ void __launch_bounds__(kCThreads, 2) gather_c(const __nv_bfloat16* __restrict__ value_t, const Desc* __restrict__ desc,
+                                                          const int* __restrict__ ppad, __nv_bfloat16* __restrict__ out, int N) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int grp = threadIdx.x >> 2, gl = threadIdx.x & 3, col = gl >> 1;
+    const int total = N * M * kCRanges;
+    const int per = (Lq + kCRanges - 1) / kCRanges;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nm = t / kCRanges, rg = t % kCRanges;
+        const int n = nm / M, m = nm % M;
+        const char* base = reinterpret_cast<const char*>(value_t) + ((size_t)nm * S) * D * 2;
+        __syncthreads();
+        // zero everything, then copy the three levels into their padded frames (16 B per thread and step)
+        for (int i = threadIdx.x; i < kPadBytes / 16; i += kCThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        int soff = 0, pstart = hs(0) * ws(0);
+#pragma unroll
+        for (int l = 1; l < L; ++l) {
+            const int H = hs(l), W = ws(l);
+            for (int i = threadIdx.x; i < H * W * 4; i += kCThreads) {
+                const int c = i & 3, pxl = i >> 2, y = pxl / W, x = pxl - y * W;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)(pstart + pxl)) * 64) + c);
+                *reinterpret_cast<uint4*>(smem + soff + ((y + 1) * (W + 2) + x + 1) * 64 + c * 16) = v;
+            }
+            soff += (H + 2) * (W + 2) * 64;
+            pstart += H * W;
+        }
+        __syncthreads();
+        const char* fb = base + gl * 32;
+        for (int it = 0; it < (per + kCThreads / 4 - 1) / (kCThreads / 4); ++it) {      // same trip count for every lane
+            const int q0 = rg * per + it * (kCThreads / 4) + grp;
+            const bool live = q0 < min(Lq, rg * per + per);
+            const int q = live ? q0 : 0;
+            const Desc* dq = desc + (((size_t)n * Lq + q) * M + m) * LP;
+            const int* pq = ppad + (((size_t)n * Lq + q) * M + m) * LP;
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            // level 0: global, as in B
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                const Desc d = dq[s];
+                const int pix = (int)(d.pix_flags & 0x0fffffffu) - 65536;
+                const char* p0 = fb + (long long)pix * 64;
+                const char* p2 = p0 + ws(0) * 64;
+                U8 rt, rb;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rt.w[i] = rb.w[i] = 0u;
+                if ((d.pix_flags >> (28 + col)) & 1u) rt = ld256(p0);
+                if ((d.pix_flags >> (30 + col)) & 1u) rb = ld256(p2);
+                const float cw = col ? d.lw : 1.f - d.lw;
+                const float wt = d.a * (1.f - d.lh) * cw, wb = d.a * d.lh * cw;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    fma2(acc[2 * i], acc[2 * i + 1], wt, rt.w[i]);
+                    fma2(acc[2 * i], acc[2 * i + 1], wb, rb.w[i]);
+                }
+            }
+            // levels 1..3: shared memory, zero border instead of corner flags
+#pragma unroll
+            for (int l = 1; l < L; ++l) {
+                const int W = ws(l);
+#pragma unroll
+                for (int pt = 0; pt < P; ++pt) {
+                    const Desc d = dq[l * P + pt];
+                    // byte offset of the top-left corner in the padded frames (precomputed: (h_lo+1)*(W+2) + (w_lo+1);
+                    // a rejected sample has weight 0 and reads the frame's first pixels)
+                    const unsigned char* p0 = smem + pq[l * P + pt] * 64 + gl * 32;
+                    const unsigned char* p2 = p0 + (W + 2) * 64;
+                    const uint4 t0 = *reinterpret_cast<const uint4*>(p0), t1 = *reinterpret_cast<const uint4*>(p0 + 16);
+                    const uint4 b0 = *reinterpret_cast<const uint4*>(p2), b1 = *reinterpret_cast<const uint4*>(p2 + 16);
+                    const float cw = col ? d.lw : 1.f - d.lw;
+                    const float wt = d.a * (1.f - d.lh) * cw, wb = d.a * d.lh * cw;
+                    const uint32_t tw[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                    const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        fma2(acc[2 * i], acc[2 * i + 1], wt, tw[i]);
+                        fma2(acc[2 * i], acc[2 * i + 1], wb, bw[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 2);
+            if (col == 0 && live) {
+                U8 o;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+                    o.w[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + ((((size_t)n * Lq + q) * M + m) * D) * 2 + gl * 32);
+                dst[0] = make_uint4(o.w[0], o.w[1], o.w[2], o.w[3]);
+                dst[1] = make_uint4(o.w[4], o.w[5], o.w[6], o.w[7]);
+            }
+        }
+    }
+}
+
 // T: [n][s][m][d] -> [n][m][s][d], 16 bytes per thread
 __global__ void transpose_heads(const uint4* __restrict__ in, uint4* __restrict__ out, int N) {
     const size_t total = (size_t)N * S * M * 4;              // 4 x 16 B per 64-byte row
@@ -176,6 +284,9 @@ int main(int argc, char** argv) {
     // descriptors with the bench's "encoder" distribution: reference point = the query's own pixel centre, offsets =
     // compass direction of the head times (p+1) pixels + N(0, 1 px)
     std::vector<Desc> hd((size_t)N * Lq * M * LP);
+    std::vector<int> hp((size_t)N * Lq * M * LP, 0);          // variant C: pixel offset in the padded shared-memory frames
+    int padstart[L] = {0, 0, 0, 0};
+    for (int l = 2; l < L; ++l) padstart[l] = padstart[l - 1] + (HS[l - 1] + 2) * (WS[l - 1] + 2);
     std::vector<float> rx(Lq), ry(Lq);
     for (int l = 0, q = 0; l < L; ++l)
         for (int y = 0; y < HS[l]; ++y)
@@ -198,6 +309,7 @@ int main(int argc, char** argv) {
                             const unsigned flags = (t & lft) | ((t & rgt) << 1) | ((b & lft) << 2) | ((b & rgt) << 3);
                             d.pix_flags = (flags << 28) | (uint32_t)(lstart[l] + h0 * WS[l] + w0 + 65536);
                             d.lh = him - h0; d.lw = wim - w0; d.a = 1.f / LP;
+                            if (l >= 1) hp[((((size_t)n * Lq + q) * M + m) * L + l) * P + p] = padstart[l] + (h0 + 1) * (WS[l] + 2) + (w0 + 1);
                         }
                         hd[((((size_t)n * Lq + q) * M + m) * L + l) * P + p] = d;
                     }
@@ -237,7 +349,23 @@ int main(int argc, char** argv) {
            "T transpose [S][M][D] -> [M][S][D]");
     timeit([&] { gather_a<<<grid, kThreads>>>(value, desc, lw, out_a, N); }, "A [S][M][D], 4 lanes x 128 bit x 4 corners");
     timeit([&] { gather_b<<<grid, kThreads>>>(value_t, desc, lw, out_b, N); }, "B [M][S][D], 4 lanes x 256 bit x 2 corner pairs");
+    __nv_bfloat16* out_c;
+    CK(cudaMalloc(&out_c, obytes));
+    int* ppad;
+    CK(cudaMalloc(&ppad, hp.size() * sizeof(int)));
+    CK(cudaMemcpy(ppad, hp.data(), hp.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(gather_c, cudaFuncAttributeMaxDynamicSharedMemorySize, kPadBytes));
+    timeit([&] { gather_c<<<sms * 2, kCThreads, kPadBytes>>>(value_t, desc, ppad, out_c, N); },
+           "C [M][S][D], level 0 as B, levels 1-3 staged in shared memory (zero border)");
     CK(cudaGetLastError());
+    {
+        std::vector<__nv_bfloat16> hb2(obytes / 2), hc(obytes / 2);
+        CK(cudaMemcpy(hb2.data(), out_b, obytes, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hc.data(), out_c, obytes, cudaMemcpyDeviceToHost));
+        double md = 0;
+        for (size_t i = 0; i < hc.size(); ++i) md = fmax(md, fabs((double)__bfloat162float(hb2[i]) - (double)__bfloat162float(hc[i])));
+        printf("{\"max_abs_diff_B_vs_C\": %.3g}\n", md);
+    }
     std::vector<__nv_bfloat16> ha(obytes / 2), hb(obytes / 2);
     CK(cudaMemcpy(ha.data(), out_a, obytes, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hb.data(), out_b, obytes, cudaMemcpyDeviceToHost));
