@@ -47,6 +47,25 @@ WORKLOAD = ("SOC Video-Swin-T deformable encoder, A2D-Sentences shape: 16 frames
             "5100 tokens/frame (48x80,24x40,12x20,6x10), 8 heads x 32, 4 levels x 4 points, Lq = S")
 
 
+# stdout carries the result line and nothing else: libraries that print there (NCCL's version banner under
+# NCCL_DEBUG=VERSION/WARN, for one) are sent to stderr for the duration of the run
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def peaks():
     try:
         with open(ROOT / "MEASURED_PEAKS.json") as f:
@@ -137,7 +156,7 @@ def run_reference(args):
     qps = x.num_queries / sec
     sample = (f"{args.ref_frames} of the 16 frames per step ({x.num_queries} queries), fp32, forward + autograd backward "
               f"through F.grid_sample on {threads} host threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -145,7 +164,7 @@ def run_reference(args):
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 # --------------------------------------------------------------------------------------------
@@ -163,7 +182,6 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -324,7 +342,7 @@ def run_ours(args):
                         "ms": sec * 1e3}
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
@@ -337,7 +355,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(),
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
@@ -354,6 +372,7 @@ def main():
                     help="frames of the step the CPU formulation is timed on (default: the whole step)")
     ap.add_argument("--e2e-frames-per-chunk", type=int, default=4)
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         if args.steps == 200:
             args.steps = 10
