@@ -151,10 +151,19 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     fn, kind = cpu_formulation(threads)
     x = make_inputs(N=args.ref_frames, dist="encoder", seed=0)
-    ts = [time_cpu(fn, x, 0, warm=False) for _ in range(args.warmup + max(1, args.steps))][args.warmup:]
+    passes = args.warmup + max(1, args.steps)
+    # bounded sample: one untimed pass over the whole step sizes the run; when `passes` of them would not end
+    # within --ref-budget-s, a step becomes the first `frames` frames of the same workload (frames are independent,
+    # queries/s is per frame) -- never fewer than one frame
+    t_full = time_cpu(fn, x, 0, warm=False)
+    frames = args.ref_frames
+    if passes * t_full > args.ref_budget_s:
+        frames = max(1, min(args.ref_frames, int(args.ref_frames * args.ref_budget_s / (passes * t_full))))
+        x = make_inputs(N=frames, dist="encoder", seed=0)
+    ts = [time_cpu(fn, x, 0, warm=False) for _ in range(passes)][args.warmup:]
     sec = sum(ts) / len(ts)
     qps = x.num_queries / sec
-    sample = (f"{args.ref_frames} of the 16 frames per step ({x.num_queries} queries), fp32, forward + autograd backward "
+    sample = (f"{frames} of the 16 frames per step ({x.num_queries} queries), fp32, forward + autograd backward "
               f"through F.grid_sample on {threads} host threads")
     emit({
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -363,21 +372,25 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="default: 200 (10 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-repeats", type=int, default=5)
     ap.add_argument("--ref-frames", type=int, default=FRAMES_PER_GPU,
                     help="frames of the step the CPU formulation is timed on (default: the whole step)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: wall-clock bound of the whole run; steps shrink to fewer frames beyond it")
     ap.add_argument("--e2e-frames-per-chunk", type=int, default=4)
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
-        if args.steps == 200:
+        if args.steps is None:
             args.steps = 10
         run_reference(args)
     else:
+        if args.steps is None:
+            args.steps = 200
         run_ours(args)
 
 
