@@ -122,3 +122,39 @@ def test_host_pipeline_chunk_plan_and_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU path"):
             host_frames.HostFramePipeline("cuda:0")
+
+
+def _run_bench(*flags, env=None):
+    import json
+    import os
+    import subprocess
+    import sys
+    e = dict(os.environ, **(env or {}))
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *flags], capture_output=True, text=True, env=e, timeout=600)
+    return r.returncode, [json.loads(ln) for ln in r.stdout.splitlines() if ln.strip()], r.stdout, r.stderr
+
+
+def test_bench_reference_arm_line_and_bounded_sample():
+    """bench.py --impl reference (the CPU formulation on the host cores): one JSON line on stdout with the arm's
+    contract keys; a run that would exceed its time bound shrinks a step to fewer frames and says so; ranks other
+    than 0 print nothing and exit 0."""
+    rc, lines, out, _ = _run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-frames", "2")
+    assert rc == 0 and len(lines) == 1 and out.count("\n") == 1
+    d = lines[0]
+    assert d["impl"] == "reference" and d["metric"] == "msdeformattn_fwd_bwd_queries_per_sec" and d["unit"] == "queries/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["sample"].startswith("2 of the 16 frames")
+    rc, lines, _, _ = _run_bench("--impl", "reference", "--steps", "2", "--warmup", "0", "--ref-frames", "3",
+                                 "--ref-budget-s", "0.001")
+    assert rc == 0 and lines[0]["cpu_baseline"]["sample"].startswith("1 of the 16 frames")
+    rc, lines, out, _ = _run_bench("--impl", "reference", "--steps", "1", env={"RANK": "1", "WORLD_SIZE": "2"})
+    assert rc == 0 and out == ""
+
+
+def test_bench_own_arm_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rc, lines, _, err = _run_bench("--steps", "1")
+    assert rc != 0 and not lines and "no CPU fallback" in err
