@@ -14,28 +14,39 @@
 #include <vector>
 #include <type_traits>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "../../include/msda_b200.h"
 #include "msda_backward.cuh"
 #include "msda_forward.cuh"
+#include "msda_host.h"
+
+// ------------------------------------------------------------------------------------------
+// helpers shared with the other translation units (msda_host.h)
+namespace msda_host {
 
 namespace {
-
-using namespace msda;
-
 thread_local std::string g_error;
-thread_local int g_launches = 0;
+std::atomic<int> g_launches{0};
 
 // Optional per-kernel timing (bench.py's roofline leg): when enabled, every launch is bracketed
 // by CUDA events on the launching stream; msda_profile_read() turns them into milliseconds.
+// Process-wide (the backward of an autograd function runs on autograd's own thread).
 struct ProfRec {
     const char* name;
     cudaEvent_t a, b;
 };
-thread_local bool g_prof = false;
-thread_local std::vector<ProfRec> g_recs;
+std::mutex g_prof_mu;
+std::atomic<bool> g_prof{false};
+std::vector<ProfRec> g_recs;
+}  // namespace
 
 void prof_begin(cudaStream_t st, const char* name) {
-    if (!g_prof) return;
+    if (!g_prof.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfRec r{name, nullptr, nullptr};
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
@@ -43,7 +54,9 @@ void prof_begin(cudaStream_t st, const char* name) {
     g_recs.push_back(r);
 }
 void prof_end(cudaStream_t st) {
-    if (g_prof && !g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+    if (!g_prof.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -56,30 +69,7 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define MSDA_CUDA(call)                                                                   \
-    do {                                                                                  \
-        cudaError_t e_ = (call);                                                          \
-        if (e_ != cudaSuccess)                                                            \
-            return fail(MSDA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
-    } while (0)
-
-#define MSDA_LAUNCHED(name)                                                               \
-    do {                                                                                  \
-        ++g_launches;                                                                     \
-        cudaError_t e_ = cudaGetLastError();                                              \
-        if (e_ != cudaSuccess)                                                            \
-            return fail(MSDA_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
-    } while (0)
-
-size_t dtype_size(int dt) {
-    switch (dt) {
-        case MSDA_F32: return 4;
-        case MSDA_BF16: return 2;
-        case MSDA_F16: return 2;
-        case MSDA_F64: return 8;
-        default: return 0;
-    }
-}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -92,14 +82,46 @@ int num_sms() {
     return cached > 0 ? cached : 148;
 }
 
-template <typename K>
-int blocks_per_sm(K kernel, int threads) {
+int blocks_per_sm_cached(const void* kernel, int threads, size_t dyn_smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<const void*, int, int, size_t>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple(kernel, dev, threads, dyn_smem);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) return it->second;
+    }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n < 1) {
         cudaGetLastError();
         n = 1;
     }
+    std::lock_guard<std::mutex> lk(mu);
+    cache[key] = n;
     return n;
+}
+
+}  // namespace msda_host
+
+namespace {
+
+using namespace msda;
+using msda_host::fail;
+using msda_host::num_sms;
+using msda_host::persistent_grid;
+using msda_host::prof_begin;
+using msda_host::prof_end;
+
+size_t dtype_size(int dt) {
+    switch (dt) {
+        case MSDA_F32: return 4;
+        case MSDA_BF16: return 2;
+        case MSDA_F16: return 2;
+        case MSDA_F64: return 8;
+        default: return 0;
+    }
 }
 
 int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -176,13 +198,6 @@ int rounds_for(int G, int Lq) {
     const int full = kTileQ / NG;
     const int need = ceil_div(Lq, NG);
     return need < full ? need : full;
-}
-
-template <typename K>
-int persistent_grid(K kernel, int threads, long long work_items) {
-    const long long cap = (long long)num_sms() * blocks_per_sm(kernel, threads);
-    long long g = work_items < cap ? work_items : cap;
-    return (int)(g < 1 ? 1 : g);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,7 +398,7 @@ int launch_grad_value_direct(const Params& p, cudaStream_t st) {
     prof_begin(st, "memset(grad_value)");
     MSDA_CUDA(cudaMemsetAsync(p.grad_value, 0, (size_t)p.N * p.S * p.M * p.D * sizeof(T), st));
     prof_end(st);
-    ++g_launches;
+    msda_host::count_launch();
     auto k = msda_grad_value_direct_kernel<T, TA, VEC, G>;
     const int K = 1 << ceil_log2(4LL * p.Lq * p.P);
     prof_begin(st, "msda_grad_value_direct_kernel");
@@ -461,7 +476,9 @@ int dispatch_bwd_sample_tile(const Params& p, const Plan& pl, int vdt, cudaStrea
 bool direct_call(int S, int Lq, int P, unsigned flags) {
     if (flags & (MSDA_FLAG_WALK_DENSE | MSDA_FLAG_ATOMIC_GRAD_VALUE | MSDA_FLAG_GENERIC)) return false;
     if (4LL * Lq * P > kDirectMax) return false;
-    return ceil_log2(S) + ceil_log2((long long)Lq * P) + 2 <= 32;      // pixel | sample | corner in one 32-bit key
+    // pixel | sample | corner in one 32-bit key; strictly fewer than 32 bits so that no real key equals the
+    // "no contribution" sentinel ~0u
+    return ceil_log2(S) + ceil_log2((long long)Lq * P) + 2 < 32;
 }
 
 template <typename TA>
@@ -548,11 +565,11 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
             prof_begin(st, "memset(bin table)");
             MSDA_CUDA(cudaMemsetAsync(p.bin_off, 0, table_bytes, st));
             prof_end(st);
-            ++g_launches;
+            msda_host::count_launch();
             if ((rc = launch_count_scan<TA, CT>(p, true, st))) return rc;
         }
         MSDA_CUDA(cudaMemsetAsync(p.counts, 0, 4 * sizeof(uint32_t), st));
-        ++g_launches;
+        msda_host::count_launch();
     }
     if (tile) {
         if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
@@ -563,6 +580,10 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
         if (!atomic_arm && (rc = launch_fill<TA, CT>(p, st))) return rc;
     }
     if (atomic_arm) return MSDA_OK;
+    if (tile && !(p.flags & MSDA_FLAG_WALK_V1)) {
+        // sort + sum in one kernel over shared-memory staged tiles (msda_grad_value_tile.cuh)
+        return msda_host::launch_grad_value_tile(p, vdt, vdt == MSDA_F32 ? 4 : 8, vdt == MSDA_F32 ? p.D / 4 : p.D / 8, st);
+    }
     if ((rc = launch_sort<CT>(p, st))) return rc;
     if (tile) return dispatch_grad_value_walk(p, pl, vdt, st);
     return launch_grad_value_generic<T, CT>(p, st);
@@ -575,27 +596,29 @@ extern "C" {
 
 int msda_version(void) { return MSDA_VERSION; }
 
-const char* msda_last_error(void) { return g_error.c_str(); }
+const char* msda_last_error(void) { return msda_host::g_error.c_str(); }
 
-int msda_last_launch_count(void) { return g_launches; }
+int msda_last_launch_count(void) { return msda_host::g_launches.load(); }
 
 void msda_profile_enable(int on) {
-    for (auto& r : g_recs) {
+    std::lock_guard<std::mutex> lk(msda_host::g_prof_mu);
+    for (auto& r : msda_host::g_recs) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
-    g_recs.clear();
-    g_prof = on != 0;
+    msda_host::g_recs.clear();
+    msda_host::g_prof.store(on != 0);
 }
 
 int msda_profile_read(char* names, size_t names_cap, float* ms, int cap) {
+    std::lock_guard<std::mutex> lk(msda_host::g_prof_mu);
     int n = 0;
     size_t used = 0;
     if (names && names_cap) names[0] = 0;
-    for (auto& r : g_recs) {
+    for (auto& r : msda_host::g_recs) {
         if (n >= cap) break;
         float t = 0.f;
-        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = -1.f;
+        if (!r.b || cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) t = -1.f;
         ms[n] = t;
         const size_t len = strlen(r.name);
         if (names && used + len + 2 <= names_cap) {
@@ -621,7 +644,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
                         size_t index_size, const void* reference_points, void* loc_out, void* attn_out, int N, int S,
                         int M, int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
                         void* cuda_stream, unsigned flags) {
-    g_launches = 0;
+    msda_host::g_launches.store(0);
     const bool fused = reference_points != nullptr;
     if (fused) {   // the raw offsets / logits may be bf16 next to fp32 values only through the value dtype rule below
         if (!loc_out || !attn_out) return fail(MSDA_ERR_INVALID_ARGUMENT, "null sampling_loc / attn_weight output");
@@ -653,7 +676,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
         prof_begin(st, "memset(index)");
         MSDA_CUDA(cudaMemsetAsync(index, 0, need, st));
         prof_end(st);
-        ++g_launches;
+        msda_host::count_launch();
     }
 
     Plan pl = make_plan(D, P, value_dtype, flags);
@@ -743,7 +766,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
                          unsigned flags, bool chain) {
-    g_launches = 0;
+    msda_host::g_launches.store(0);
     flags &= ~kFlagChain;
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
@@ -787,7 +810,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
         p.entries = base + w.entries;
     } else {
         MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)N * S * M * D * dtype_size(value_dtype), st));
-        ++g_launches;
+        msda_host::count_launch();
     }
 
     if (pl.tile && !(aligned16(value) && aligned16(grad_output) && aligned16(grad_value) && aligned16(sampling_loc) &&

@@ -43,16 +43,6 @@
 namespace msda {
 
 
-template <typename CT> struct Entry;
-template <> struct __align__(16) Entry<float> {
-    uint32_t id;
-    float lh, lw, a;
-};
-template <> struct __align__(16) Entry<double> {
-    uint32_t id, pad;
-    double lh, lw, a;
-};
-
 // =========================================================================================
 // A. grad_sampling_loc, grad_attn_weight
 // =========================================================================================
@@ -125,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
     stage_load<TA, G, P>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, tl, cur, desc[0]);
+    stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, tl, cur, desc[0], index_usable(p, s_sb));
     __syncthreads();
 
     int buf = 0;
@@ -323,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
             }
         }
 
-        if (has_next) stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        if (has_next) stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, ntl, nxt, desc[buf ^ 1], index_usable(p, s_sb));
         __syncthreads();
         if (!has_next) break;
         cur = nxt;
@@ -421,6 +411,7 @@ __global__ void __launch_bounds__(kThreads) msda_bin_count_kernel(const Params p
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     load_levels(p, lv, &s_sb, &s_sq);
+    if (!index_usable(p, s_sb)) return;
     const TA* __restrict__ loc = static_cast<const TA*>(p.loc);
     const size_t total = (size_t)p.N * p.Lq * p.M * p.LP;
     for (size_t si = (size_t)blockIdx.x * blockDim.x + threadIdx.x; si < total; si += (size_t)gridDim.x * blockDim.x) {
@@ -491,6 +482,7 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     load_levels(p, lv, &s_sb, &s_sq);
+    if (!index_usable(p, s_sb)) return;
     const TA* __restrict__ loc = static_cast<const TA*>(p.loc);
     const TA* __restrict__ attn = static_cast<const TA*>(p.attn);
     Entry<CT>* __restrict__ entries = static_cast<Entry<CT>*>(p.entries);
@@ -527,7 +519,6 @@ __global__ void __launch_bounds__(kThreads) msda_bin_fill_kernel(const Params p)
 #define MSDA_RANK_STAGE_BYTES 16384
 #endif
 constexpr int kRankSpan = MSDA_RANK_SPAN;   // sub-bins staged per step (at most)
-constexpr int kRankMax = 512;    // largest sub-bin ranked by counting
 
 template <typename CT>
 __global__ void __launch_bounds__(kThreads) msda_bin_rank_sort_kernel(const Params p) {
@@ -741,6 +732,7 @@ __global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_
     __shared__ __align__(16) float sT[TH * TW * D];
     __shared__ __align__(16) float sB[TH * TW * D];
     load_levels(p, lv, &s_sb, &s_sq);
+    if (!index_usable(p, s_sb)) return;
     auto is_dense = [&](const int l) { return GW > 1 && lv[l].nch_log2 >= 3; };
     auto tiles_of = [&](const int l) {
         const int th = is_dense(l) ? TH_D : TH, tw = is_dense(l) ? TW_D : TW;
@@ -1075,6 +1067,7 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_generic_kernel(const
     __shared__ Level lv[kMaxLevels];
     __shared__ int s_sb, s_sq;
     load_levels(p, lv, &s_sb, &s_sq);
+    if (!index_usable(p, s_sb)) return;
     const T* __restrict__ gout = static_cast<const T*>(p.grad_out);
     T* __restrict__ gval = static_cast<T*>(p.grad_value);
     const Entry<CT>* __restrict__ entries = static_cast<const Entry<CT>*>(p.entries);

@@ -27,6 +27,7 @@ constexpr int kMaxSubLog2 = 8;
 constexpr int kTileW = 16;       // pyramid query tile: kTileH x kTileW pixels of one level
 constexpr int kTileH = 8;
 constexpr int kTileQ = kTileW * kTileH;
+constexpr int kRankMax = 512;    // largest sub-bin ranked by counting (larger ones are sorted in place beforehand)
 
 // Everything a kernel needs; passed by value.
 struct Params {
@@ -67,6 +68,18 @@ struct Level {
     int bin_start;  // first sub-bin of the level
     int nch_log2;   // log2(sub-bins per bin)
     int pad[3];
+};
+
+// One entry of the inverse index of the grad_value gather (msda_backward.cuh, part B):
+// query | sample id, the sample's fractional position and its attention weight.
+template <typename CT> struct Entry;
+template <> struct __align__(16) Entry<float> {
+    uint32_t id;
+    float lh, lw, a;
+};
+template <> struct __align__(16) Entry<double> {
+    uint32_t id, pad;
+    double lh, lw, a;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -364,11 +377,17 @@ __device__ __forceinline__ void load_levels(const Params& p, Level* lv, int* sb,
             b += (int)(nb << k);
             q += lv[l].H * lv[l].W;
         }
-        *sb = b;
+        // The table holds p.sb_max sub-bins (host bound, msda_api.cu: sub_bin_bound, valid when sum_l H_l*W_l <= S).
+        // Shapes that disagree with S would overflow it: such a call keeps no index at all (*sb = 0: nothing is
+        // counted, filled or walked; grad_value is then left unwritten -- the reference reads out of bounds here).
+        *sb = (p.sb_max > 0 && b > p.sb_max) ? 0 : b;
         *sq = q;
     }
     __syncthreads();
 }
+
+// false when load_levels() found the level table inconsistent with the index buffer (see there)
+__device__ __forceinline__ bool index_usable(const Params& p, const int sb) { return p.sb_max <= 0 || sb > 0; }
 
 // ---------------------------------------------------------------------------------------
 // Query tiles.  A tile is a set of up to kTileQ queries of one (frame, head) handled by

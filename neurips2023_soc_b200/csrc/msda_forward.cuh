@@ -68,7 +68,7 @@ msda_fwd_tile_kernel(const Params p, const int rounds) {
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
     stage_load<TA, G, P, FUSED>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, MODE, FUSED>(st, p, lv, tl, cur, desc[0]);
+    stage_build<G, P, MODE, FUSED>(st, p, lv, tl, cur, desc[0], index_usable(p, s_sb));
     __syncthreads();
 
     int buf = 0;
@@ -138,7 +138,7 @@ msda_fwd_tile_kernel(const Params p, const int rounds) {
                 store_row<T, VEC>(out + (((size_t)tl.n * p.Lq + q_mine) * p.M + tl.m) * p.D + gl * VEC, acc);
         }
 
-        if (has_next) stage_build<G, P, MODE, FUSED>(st, p, lv, ntl, nxt, desc[buf ^ 1]);
+        if (has_next) stage_build<G, P, MODE, FUSED>(st, p, lv, ntl, nxt, desc[buf ^ 1], index_usable(p, s_sb));
         __syncthreads();
         if (!has_next) break;
         cur = nxt;

@@ -131,7 +131,8 @@ constexpr int kIndexNone = 0, kIndexCount = 1, kIndexFill = 2;
 
 template <int G, int P, int MODE, bool FUSED = false>
 __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
-                                            const Tile& tl, const Work& w, uint4* __restrict__ desc) {
+                                            const Tile& tl, const Work& w, uint4* __restrict__ desc,
+                                            const bool index_ok = true) {
     constexpr int DPT = TileShape<G>::DPT;
     if constexpr (FUSED) fused_prologue<G, P>(st, p, lv, tl, w);
     const int st_s = threadIdx.x % kSC, st_j0 = threadIdx.x / kSC;
@@ -139,7 +140,9 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
     const int l = min(sg / P, p.L - 1);
     const Level L_ = lv[l];
     const size_t nm = (size_t)tl.n * p.M + tl.m;
-    const bool fill = MODE == kIndexFill && p.entries != nullptr;   // null: the direct gather follows, no index is kept
+    // null entries: the direct gather follows, no index is kept; !index_ok: the level table does not fit the
+    // index buffer (msda_common.cuh: load_levels), nothing may be written
+    const bool fill = MODE == kIndexFill && p.entries != nullptr && index_ok;
     // With 4 descriptors per thread (4-lane rows) the slot atomics of a thread are issued together and the entries
     // written in a second pass: waiting for each atomic's return in turn was 23 % of the sample-gradient kernel's
     // stall samples (300 -> 288 us).  With 2 per thread (8-lane rows) the extra live registers cost more (fp32
@@ -168,7 +171,7 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
                     // slot b+1 of the table row belongs to sub-bin b (see msda_bin_scan_kernel)
                     const size_t b = nm * (p.sb_max + 1) + sub_bin(L_, s.h_lo, s.w_lo, st.q[k]) + 1;
                     if constexpr (MODE == kIndexCount) {
-                        atomicAdd(p.bin_off + b, 1u);
+                        if (index_ok) atomicAdd(p.bin_off + b, 1u);
                     } else if (fill) {
                         slot[k] = atomicAdd(p.bin_off + b, 1u);
                         live[k] = true;

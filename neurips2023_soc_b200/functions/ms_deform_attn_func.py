@@ -80,6 +80,9 @@ class MSDeformAttnFusedFunction(Function):
                 attention_logits, im2col_step):
         ctx.im2col_step = im2col_step
         ctx.in_dtypes = (sampling_offsets.dtype, attention_logits.dtype, reference_points.dtype)
+        # undefined gradients of the returned locations / weights must arrive as None, not as zero tensors:
+        # that is how backward() knows nobody differentiated through them and takes the in-kernel chain rule
+        ctx.set_materialize_grads(False)
         raw = sampling_offsets.dtype if (sampling_offsets.dtype == attention_logits.dtype and
                                          sampling_offsets.dtype in (value.dtype, torch.float32)) else torch.float32
         value = value.contiguous()
@@ -97,6 +100,8 @@ class MSDeformAttnFusedFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output, grad_loc_out, grad_attn_out):
         value, shapes, lsi, loc, attn = ctx.saved_tensors
+        if grad_output is None:               # only the returned locations / weights were differentiated
+            grad_output = value.new_zeros((value.shape[0], loc.shape[1], value.shape[2] * value.shape[3]))
         go = grad_output.to(value.dtype).contiguous()
         index, ctx.index = ctx.index, None
         if grad_loc_out is None and grad_attn_out is None:

@@ -428,11 +428,19 @@ def test_module_fused_prologue_matches_unfused(amp):
                 w = torch.softmax(mod.attention_weights(query).view(N, Lq, 8, 16).float(), -1).view(N, Lq, 8, 4, 4)
                 loc = ref[:, :, None, :, None, :] + off / shapes.flip(-1)[None, None, None, :, None, :]
                 out = mod.output_proj(MSDeformAttnFunction.apply(value, shapes, lsi, loc, w, 64))
+        _lib.profile_enable(True)              # process-wide: sees the kernels autograd's thread launches
         (out.float() * g).sum().backward()
+        torch.cuda.synchronize()
+        kernels = [name for name, _ in _lib.profile_read()]
+        _lib.profile_enable(False)
         grads = [p.grad.clone() for p in mod.parameters()] + [query.grad.clone(), src.grad.clone(), ref.grad.clone()]
-        return out.detach().float(), loc.detach().float(), w.detach().float(), grads
+        return out.detach().float(), loc.detach().float(), w.detach().float(), grads, kernels
 
     a, b = run(True), run(False)
+    # nobody differentiates through the returned locations / weights here, so the fused module must take the
+    # in-kernel chain rule (msda_backward_fused), the unfused one the plain sample-gradient kernel
+    assert "msda_bwd_sample_tile_kernel<chain>" in a[4], a[4]
+    assert "msda_bwd_sample_tile_kernel" in b[4] and "msda_bwd_sample_tile_kernel<chain>" not in b[4], b[4]
     tol = 3e-2 if amp else 2e-5
     assert a[1].dtype == torch.float32 and a[1].shape == (N, Lq, 8, 4, 4, 2)
     assert float((a[1] - b[1]).abs().max()) <= 1e-6                          # sampling locations
@@ -573,3 +581,65 @@ def test_backward_fused_rejects_what_it_has_no_kernel_for():
     with pytest.raises(RuntimeError, match="fused prologue"):
         msda_ext.ms_deform_attn_backward_fused(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
                                                x.attention_weights, x.grad_output, 64)
+
+
+# ---------------------------------------------------------------------------- grad_value tile kernel (part B, 2nd generation)
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("kw", [
+    dict(N=2, dist="encoder"),                                                               # the A2D pyramid
+    dict(N=1, dist="uniform"),                                                               # adversarial locations
+    dict(N=1, dist="encoder", shapes=[(50, 77), (25, 39), (13, 20), (7, 10)]),               # tiles that do not divide
+    dict(N=2, dist="uniform", shapes=[(9, 11)], M=3, D=64, Lq=700, P=8),                     # D = 64, P = 8, one level
+    dict(N=1, dist="uniform", shapes=[(3, 4), (1, 2)], M=2, D=32, Lq=3000, P=4),             # dense tiny maps: long bins
+])
+def test_grad_value_tile_kernel_vs_first_generation(kw, vdt, adt):
+    """The shared-memory tile kernel (default) and the rank-sort + row-walker pair (MSDA_FLAG_WALK_V1) sum the same
+    terms in different orders: they agree to rounding, both agree with the fp64 oracle, and part A's results are
+    the same bits either way."""
+    x = make_inputs(seed=81, **kw)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    new = run_op(*a, vdt, adt)
+    old = run_op(*a, vdt, adt, flags=_lib.FLAG_WALK_V1)
+    v, lo, at, go = new[4]
+    r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
+    tol = TOL[vdt]
+    assert rel_err(new[1], r_gv) <= tol
+    assert rel_err(old[1], r_gv) <= tol
+    assert torch.equal(new[0], old[0]) and torch.equal(new[2], old[2]) and torch.equal(new[3], old[3])
+
+
+def test_grad_value_tile_kernel_bf16_wide_rows():
+    """bf16 rows of 128 and 256 bytes (D = 64, 128): 8 and 16 lanes x 128 bit per row."""
+    for D in (64, 128):
+        x = make_inputs(N=1, dist="uniform", shapes=[(10, 12), (5, 6)], M=2, D=D, Lq=400, P=4, seed=82)
+        _check_against_oracle(x, torch.bfloat16, torch.float32, tol=2e-2)
+
+
+@pytest.mark.parametrize("Lq", [40000, 70000])
+def test_grad_value_tile_kernel_oversized_sub_bins(Lq):
+    """Every query samples the same spot of a 2 x 2 map: one bin holds Lq * P entries in 256 sub-bins of 625
+    (presorted in place, kept in order by the rank step) or 1094 entries (larger than one round: sliced).  Checked
+    against the fp64 oracle, and twice for bit reproducibility."""
+    x = make_inputs(N=1, dist="uniform", shapes=[(2, 2)], M=1, D=32, Lq=Lq, P=4, seed=83)
+    loc = x.sampling_locations * 0.0 + torch.tensor([0.52, 0.47])
+    loc[:, ::97] += 0.2                                       # a few elsewhere
+    res = [run_op(x.value, x.spatial_shapes, x.level_start_index, loc, x.attention_weights, x.grad_output,
+                  torch.float32, torch.float32) for _ in range(2)]
+    out, gv, gl, ga, (v, lo, at, go) = res[0]
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    assert rel_err(gv, r_gv) <= 1e-5
+    assert rel_err(ga, r_ga) <= 1e-5
+    assert torch.equal(res[0][1], res[1][1])
+
+
+def test_grad_value_tile_kernel_is_frame_independent():
+    """Tile sizes, round cuts and the sharing of dense bins depend on per-frame quantities only: a frame alone
+    reproduces its slice of the batch bit for bit (fp32 and bf16, both location distributions)."""
+    for dist, vdt in (("encoder", torch.float32), ("uniform", torch.bfloat16)):
+        x = make_inputs(N=3, dist=dist, seed=84).to(DEV, vdt, torch.float32)
+        a = (x.spatial_shapes, x.level_start_index)
+        g_all = msda_ext.ms_deform_attn_backward(x.value, *a, x.sampling_locations, x.attention_weights, x.grad_output, 64)
+        g_one = msda_ext.ms_deform_attn_backward(x.value[1:2].contiguous(), *a, x.sampling_locations[1:2].contiguous(),
+                                                 x.attention_weights[1:2].contiguous(), x.grad_output[1:2].contiguous(), 64)
+        for u, w in zip(g_one, g_all):
+            assert torch.equal(u[0], w[1])

@@ -22,6 +22,7 @@ ap.add_argument("--N", type=int, default=16)
 ap.add_argument("--dtype", default="bf16mix")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--dist", default="encoder")
+ap.add_argument("--flags", type=int, default=0, help="msda_*_ex flags (32: first-generation sort + walk)")
 a = ap.parse_args()
 vdt, adt = {"fp32": (torch.float32, torch.float32), "bf16mix": (torch.bfloat16, torch.float32)}[a.dtype]
 full = make_inputs(N=a.N, dist=a.dist, seed=0)
@@ -32,8 +33,8 @@ def times(value, shapes, lsi, loc, attn, gout):
     args = (value, shapes, lsi, loc, attn)
 
     def step():
-        _, index = msda_ext.ms_deform_attn_forward(*args, 64, want_index=True)
-        msda_ext.ms_deform_attn_backward(*args, gout, 64, index=index)
+        _, index = msda_ext.ms_deform_attn_forward(*args, 64, want_index=True, flags=a.flags)
+        msda_ext.ms_deform_attn_backward(*args, gout, 64, index=index, flags=a.flags)
     for _ in range(3):
         step()
     torch.cuda.synchronize()
