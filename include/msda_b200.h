@@ -80,8 +80,9 @@ enum msda_status {
 #define MSDA_FLAG_GENERIC 2u       /* force the any-D scalar kernels */
 #define MSDA_FLAG_ATOMIC_GRAD_VALUE 4u /* bench-only: fp32 red.global scatter (NOT deterministic) */
 #define MSDA_FLAG_BF16_VEC4 8u     /* A/B: 64-byte bf16 rows on 8 lanes x 64 bit instead of 4 lanes x 128 bit */
-#define MSDA_FLAG_WALK_V1 32u      /* A/B: grad_value through the first-generation pair (rank-sort kernel + row walker)
-                                      instead of the shared-memory tile kernel */
+#define MSDA_FLAG_BIN_KERNEL 32u   /* A/B: grad_value through the one-kernel bin pass (msda_bwd_bin.cuh: entries sorted and
+                                      summed in shared memory, half the index traffic) instead of rank-sort + row walker;
+                                      measured slower on B200, kept for comparison */
 #define MSDA_FLAG_WALK_DENSE 16u   /* force the inverse-index pipeline for grad_value even when the call is small enough
                                       for the direct shared-memory gather (decoder-shaped calls, Lq * P <= 512) */
 

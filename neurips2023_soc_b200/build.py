@@ -74,4 +74,14 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: P
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python -m neurips2023_soc_b200.build [--force] [-v] [--variant NAME -DMACRO=VALUE ...]
+    #   --variant: kernel-variant build for A/B runs -> variants/NAME.so (git-ignored, shipped by gpurun;
+    #   select with MSDA_LIB=$PWD/variants/NAME.so)
+    argv = sys.argv[1:]
+    if "--variant" in argv:
+        name = argv[argv.index("--variant") + 1]
+        out = PKG.parent / "variants" / f"{name}.so"
+        out.parent.mkdir(exist_ok=True)
+        print(build_library(force=True, verbose="-v" in argv, defines=[a[2:] for a in argv if a.startswith("-D")], out=out))
+    else:
+        print(build_library(force="--force" in argv, verbose="-v" in argv))

@@ -580,8 +580,8 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
         if (!atomic_arm && (rc = launch_fill<TA, CT>(p, st))) return rc;
     }
     if (atomic_arm) return MSDA_OK;
-    if (tile && !(p.flags & MSDA_FLAG_WALK_V1)) {
-        // sort + sum in one kernel over shared-memory staged tiles (msda_grad_value_tile.cuh)
+    if (tile && (p.flags & MSDA_FLAG_BIN_KERNEL)) {
+        // A/B: sort + sum in one kernel over shared-memory pixel tiles (msda_bwd_bin.cuh)
         return msda_host::launch_grad_value_tile(p, vdt, vdt == MSDA_F32 ? 4 : 8, vdt == MSDA_F32 ? p.D / 4 : p.D / 8, st);
     }
     if ((rc = launch_sort<CT>(p, st))) return rc;

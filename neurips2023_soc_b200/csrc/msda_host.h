@@ -1,5 +1,5 @@
 // msda_host.h -- host-side helpers shared by the translation units of libmsda_b200.so
-// (msda_api.cu: C ABI + dispatch; msda_grad_value_tile.cu: the grad_value tile kernels).
+// (msda_api.cu: C ABI + dispatch; msda_bwd_bin.cu: the bin-major backward pass).
 // Internal: nothing here is part of the C ABI (include/msda_b200.h).
 #pragma once
 
@@ -48,7 +48,7 @@ int persistent_grid(K kernel, int threads, long long work_items, size_t dyn_smem
             return msda_host::fail(MSDA_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 
-// msda_grad_value_tile.cu: part B of the backward on the tile path (fp32 / bf16 rows): presort of oversized
+// msda_bwd_bin.cu: part B of the backward on the tile path (fp32 / bf16 rows): presort of oversized
 // sub-bins + the shared-memory tile kernel.  vdt: MSDA_F32 or MSDA_BF16; (vec, g): lanes layout of a row.
 int launch_grad_value_tile(const msda::Params& p, int vdt, int vec, int g, cudaStream_t st);
 

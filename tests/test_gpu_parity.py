@@ -583,7 +583,7 @@ def test_backward_fused_rejects_what_it_has_no_kernel_for():
                                                x.attention_weights, x.grad_output, 64)
 
 
-# ---------------------------------------------------------------------------- grad_value tile kernel (part B, 2nd generation)
+# ---------------------------------------------------------------------------- grad_value bin kernel (part B, A/B arm)
 @pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
 @pytest.mark.parametrize("kw", [
     dict(N=2, dist="encoder"),                                                               # the A2D pyramid
@@ -592,14 +592,14 @@ def test_backward_fused_rejects_what_it_has_no_kernel_for():
     dict(N=2, dist="uniform", shapes=[(9, 11)], M=3, D=64, Lq=700, P=8),                     # D = 64, P = 8, one level
     dict(N=1, dist="uniform", shapes=[(3, 4), (1, 2)], M=2, D=32, Lq=3000, P=4),             # dense tiny maps: long bins
 ])
-def test_grad_value_tile_kernel_vs_first_generation(kw, vdt, adt):
-    """The shared-memory tile kernel (default) and the rank-sort + row-walker pair (MSDA_FLAG_WALK_V1) sum the same
+def test_grad_value_bin_kernel_vs_sort_and_walk(kw, vdt, adt):
+    """The one-kernel bin pass (MSDA_FLAG_BIN_KERNEL) and the rank-sort + row-walker pair (default) sum the same
     terms in different orders: they agree to rounding, both agree with the fp64 oracle, and part A's results are
     the same bits either way."""
     x = make_inputs(seed=81, **kw)
     a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
-    new = run_op(*a, vdt, adt)
-    old = run_op(*a, vdt, adt, flags=_lib.FLAG_WALK_V1)
+    new = run_op(*a, vdt, adt, flags=_lib.FLAG_BIN_KERNEL)
+    old = run_op(*a, vdt, adt)
     v, lo, at, go = new[4]
     r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
     tol = TOL[vdt]
@@ -608,23 +608,25 @@ def test_grad_value_tile_kernel_vs_first_generation(kw, vdt, adt):
     assert torch.equal(new[0], old[0]) and torch.equal(new[2], old[2]) and torch.equal(new[3], old[3])
 
 
-def test_grad_value_tile_kernel_bf16_wide_rows():
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_BIN_KERNEL])
+def test_grad_value_bf16_wide_rows(flags):
     """bf16 rows of 128 and 256 bytes (D = 64, 128): 8 and 16 lanes x 128 bit per row."""
     for D in (64, 128):
         x = make_inputs(N=1, dist="uniform", shapes=[(10, 12), (5, 6)], M=2, D=D, Lq=400, P=4, seed=82)
-        _check_against_oracle(x, torch.bfloat16, torch.float32, tol=2e-2)
+        _check_against_oracle(x, torch.bfloat16, torch.float32, tol=2e-2, flags=flags)
 
 
-@pytest.mark.parametrize("Lq", [40000, 70000])
-def test_grad_value_tile_kernel_oversized_sub_bins(Lq):
-    """Every query samples the same spot of a 2 x 2 map: one bin holds Lq * P entries in 256 sub-bins of 625
-    (presorted in place, kept in order by the rank step) or 1094 entries (larger than one round: sliced).  Checked
-    against the fp64 oracle, and twice for bit reproducibility."""
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_BIN_KERNEL])
+@pytest.mark.parametrize("Lq", [12000, 40000, 70000])
+def test_grad_value_oversized_sub_bins(Lq, flags):
+    """Every query samples the same spot of a 2 x 2 map: one bin holds Lq * P entries in 256 sub-bins of 187
+    (sorted in place beforehand, kept in order by the rank step), 625 or 1094 entries (larger than one staging
+    chunk: sliced).  Checked against the fp64 oracle, and twice for bit reproducibility."""
     x = make_inputs(N=1, dist="uniform", shapes=[(2, 2)], M=1, D=32, Lq=Lq, P=4, seed=83)
     loc = x.sampling_locations * 0.0 + torch.tensor([0.52, 0.47])
     loc[:, ::97] += 0.2                                       # a few elsewhere
     res = [run_op(x.value, x.spatial_shapes, x.level_start_index, loc, x.attention_weights, x.grad_output,
-                  torch.float32, torch.float32) for _ in range(2)]
+                  torch.float32, torch.float32, flags=flags) for _ in range(2)]
     out, gv, gl, ga, (v, lo, at, go) = res[0]
     r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
     assert rel_err(gv, r_gv) <= 1e-5
@@ -632,14 +634,17 @@ def test_grad_value_tile_kernel_oversized_sub_bins(Lq):
     assert torch.equal(res[0][1], res[1][1])
 
 
-def test_grad_value_tile_kernel_is_frame_independent():
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_BIN_KERNEL])
+def test_grad_value_is_frame_independent(flags):
     """Tile sizes, round cuts and the sharing of dense bins depend on per-frame quantities only: a frame alone
     reproduces its slice of the batch bit for bit (fp32 and bf16, both location distributions)."""
     for dist, vdt in (("encoder", torch.float32), ("uniform", torch.bfloat16)):
         x = make_inputs(N=3, dist=dist, seed=84).to(DEV, vdt, torch.float32)
         a = (x.spatial_shapes, x.level_start_index)
-        g_all = msda_ext.ms_deform_attn_backward(x.value, *a, x.sampling_locations, x.attention_weights, x.grad_output, 64)
+        g_all = msda_ext.ms_deform_attn_backward(x.value, *a, x.sampling_locations, x.attention_weights, x.grad_output, 64,
+                                                 flags=flags)
         g_one = msda_ext.ms_deform_attn_backward(x.value[1:2].contiguous(), *a, x.sampling_locations[1:2].contiguous(),
-                                                 x.attention_weights[1:2].contiguous(), x.grad_output[1:2].contiguous(), 64)
+                                                 x.attention_weights[1:2].contiguous(), x.grad_output[1:2].contiguous(), 64,
+                                                 flags=flags)
         for u, w in zip(g_one, g_all):
             assert torch.equal(u[0], w[1])
