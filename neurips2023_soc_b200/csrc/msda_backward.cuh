@@ -732,7 +732,6 @@ __global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_
     __shared__ __align__(16) float sT[TH * TW * D];
     __shared__ __align__(16) float sB[TH * TW * D];
     load_levels(p, lv, &s_sb, &s_sq);
-    if (!index_usable(p, s_sb)) return;
     auto is_dense = [&](const int l) { return GW > 1 && lv[l].nch_log2 >= 3; };
     auto tiles_of = [&](const int l) {
         const int th = is_dense(l) ? TH_D : TH, tw = is_dense(l) ? TW_D : TW;
@@ -746,7 +745,7 @@ __global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_
             tstart[l] = t;
             t += p.N * p.M * tiles_of(l);
         }
-        tstart[p.L] = t;     // total
+        tstart[p.L] = index_usable(p, s_sb) ? t : 0;     // total (no tiles at all when the index is unusable)
     }
     __syncthreads();
 

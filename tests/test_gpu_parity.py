@@ -648,3 +648,31 @@ def test_grad_value_is_frame_independent(flags):
                                                  flags=flags)
         for u, w in zip(g_one, g_all):
             assert torch.equal(u[0], w[1])
+
+
+# ---------------------------------------------------------------------------- the benchmarked configuration itself
+def test_bench_configuration_vs_oracle_all_16_frames():
+    """bench.py's own step -- 16 frames x 5100 tokens, bf16 values, fp32 locations / weights, the index handed from
+    the forward to the backward, buffers passed in -- against the fp64 C oracle evaluated on the bf16-rounded
+    inputs, every frame (2e-2, north_star's bf16 bound)."""
+    x = make_inputs(N=16, dist="encoder", seed=0)
+    out, gv, gl, ga, (v, lo, at, go) = run_op(x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations,
+                                               x.attention_weights, x.grad_output, torch.bfloat16, torch.float32)
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    keep = off_lattice(lo.double().cpu().numpy(), x.spatial_shapes.numpy(), 1e-3)
+    worst = {}
+    for n in range(16):          # frame by frame: no frame hides behind another's larger values
+        worst["out"] = max(worst.get("out", 0.0), rel_err(out[n], r_out[n]))
+        worst["grad_value"] = max(worst.get("grad_value", 0.0), rel_err(gv[n], r_gv[n]))
+        worst["grad_attn"] = max(worst.get("grad_attn", 0.0), rel_err(ga[n], r_ga[n]))
+        worst["grad_loc"] = max(worst.get("grad_loc", 0.0), rel_err(gl[n], r_gl[n], keep[n]))
+    assert max(worst.values()) <= 2e-2, worst
+
+
+@pytest.mark.parametrize("D", [1025, 2048, 3096])
+def test_large_channel_counts_of_the_reference_test(D):
+    """models/ops/test.py:85 walks through D = 1025, 2048, 3096 to reach the reference's global-memory and
+    multi-block backward variants (cuh:731-920); here they take the any-D kernels.  fp64 against the C oracle."""
+    x = make_inputs(N=1, dist="uniform", shapes=[(6, 4), (3, 2)], M=2, D=D, Lq=2, P=2, seed=91, value_scale=0.01)
+    _check_against_oracle(x, torch.float64, torch.float64, tol=1e-11)
+    _check_against_oracle(x, torch.float32, torch.float32, tol=1e-5)

@@ -2,13 +2,16 @@
 through this repo's MSDeformAttn, FFN 2048, LayerNorms -- over 16 frames x 5100 tokens per GPU, forward +
 backward, optionally under bf16 autocast and DistributedDataParallel (gradient all-reduce over NCCL).
 
-The layer restates DeformableTransformerEncoderLayer / DeformableTransformerEncoder
-(/root/reference/models/deformable_transformer.py:225-293: self_attn(src + pos) -> residual -> LayerNorm ->
-FFN -> residual -> LayerNorm; reference points = pixel centres of every level for every query) with this
-repo's module inside; the reference file itself cannot travel to the GPU box.  Dense parts are PyTorch
-(cuBLAS); the point is the op inside its real caller: autocast dtype mix, autograd, index handoff, DDP.
+By default the encoder IS the reference's: DeformableTransformerEncoder / DeformableTransformerEncoderLayer of the
+unmodified models/deformable_transformer.py staged under baseline/_ref/soc (tools/stage_reference.py), with
+`models.ops.modules.MSDeformAttn` routed to this repo's module (--reference-module keeps the reference's own module
+and autograd function too, on this repo's two extension entry points).  --restated (or nothing staged) uses the
+small restatement below (/root/reference/models/deformable_transformer.py:225-293: self_attn(src + pos) ->
+residual -> LayerNorm -> FFN -> residual -> LayerNorm; reference points = pixel centres of every level for every
+query).  Dense parts are PyTorch (cuBLAS); the point is the op inside its real caller: autocast dtype mix,
+autograd, index handoff, DDP.
 
-    python tools/encoder_bench.py [--layers 3] [--frames 16] [--amp] [--steps 20]
+    python tools/encoder_bench.py [--layers 3] [--frames 16] [--amp] [--steps 20] [--profile]
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/encoder_bench.py --amp
 """
 import argparse
@@ -50,8 +53,31 @@ class Encoder(nn.Module):
         return src
 
 
+def reference_encoder(layers, keep_reference_module):
+    """DeformableTransformerEncoder of the staged, unmodified reference file (None when nothing is staged)."""
+    import importlib
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.join(root, "baseline", "_ref", "soc")
+    if not os.path.exists(os.path.join(staged, "MANIFEST.json")):
+        return None
+    sys.path.insert(1, staged)                 # behind the repo root: MultiScaleDeformableAttention is this repo's shim
+    if not keep_reference_module:              # deformable_transformer.py:20 `from models.ops.modules import MSDeformAttn`
+        ops = types.ModuleType("models.ops")
+        ops.__path__ = []
+        mods = types.ModuleType("models.ops.modules")
+        mods.MSDeformAttn = MSDeformAttn
+        sys.modules["models.ops"], sys.modules["models.ops.modules"] = ops, mods
+    dt = importlib.import_module("models.deformable_transformer")
+    layer = dt.DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4)
+    return dt.DeformableTransformerEncoder(layer, layers)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--restated", action="store_true", help="the small restatement of the encoder instead of the staged reference class")
+    ap.add_argument("--reference-module", action="store_true", help="keep the reference's own MSDeformAttn module / autograd function too")
+    ap.add_argument("--profile", action="store_true", help="print the step's CUDA kernels by total time (torch.profiler)")
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
@@ -72,11 +98,20 @@ def main():
     ref = pyramid_reference_points(shapes_l).to(dev)[None, :, None, :].expand(a.frames, S, len(shapes_l), 2).contiguous()
     src = torch.randn(a.frames, S, 256, device=dev)
     pos = torch.randn(a.frames, S, 256, device=dev)
-    model = Encoder(a.layers).to(dev)
+    model = None if a.restated else reference_encoder(a.layers, a.reference_module)
+    which = "reference DeformableTransformerEncoder (staged, unmodified)" + (" + reference MSDeformAttn module" if a.reference_module else "")
+    if model is None:
+        model, which = Encoder(a.layers), "restated encoder"
+        call = lambda net: net(src, pos, ref, shapes, lsi)                                    # noqa: E731
+    else:
+        ratios = torch.ones(a.frames, len(shapes_l), 2, device=dev)                           # no padding: valid ratio 1
+        call = lambda net: net(src, shapes, lsi, ratios, pos, None)                           # noqa: E731
+    model = model.to(dev)
     with torch.no_grad():          # leave the all-zero init of the offset / attention projections
         for m in model.modules():
-            if isinstance(m, MSDeformAttn):
-                m.fused_prologue = a.fuse
+            if hasattr(m, "sampling_offsets") and hasattr(m, "attention_weights"):
+                if isinstance(m, MSDeformAttn):
+                    m.fused_prologue = a.fuse
                 m.sampling_offsets.weight.normal_(0, 0.02)
                 m.attention_weights.weight.normal_(0, 0.02)
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
@@ -85,7 +120,7 @@ def main():
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
-            out = net(src, pos, ref, shapes, lsi)
+            out = call(net)
             loss = out.float().pow(2).mean()
         loss.backward()
         opt.step()
@@ -107,16 +142,22 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     # share of the step spent in this repo's kernels (main thread = forward; backward runs on autograd's thread)
     _lib.profile_enable(True)
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
-        out = net(src, pos, ref, shapes, lsi)
+    step()
     torch.cuda.synchronize()
-    fwd_ms = sum(t for _, t in _lib.profile_read())
+    fwd_ms = sum(t for _, t in _lib.profile_read())      # process-wide: forward and backward kernels of one step
     _lib.profile_enable(False)
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
     if rank == 0:
-        print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "layers": a.layers, "frames_per_gpu": a.frames,
+        print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "encoder": which, "layers": a.layers, "frames_per_gpu": a.frames,
                           "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "n_gpus": world, "ms_per_step": float(ms.item()),
                           "queries_per_s": world * a.frames * S / (float(ms.item()) * 1e-3),
-                          "msda_forward_kernels_ms": fwd_ms, "loss": float(loss)}))
+                          "msda_kernels_ms_per_step": fwd_ms, "loss": float(loss)}))
     if world > 1:
         dist.destroy_process_group()
 
