@@ -34,6 +34,19 @@ FILES = [
     "models/ops/functions/ms_deform_attn_func.py",
     "models/ops/modules/__init__.py",
     "models/ops/modules/ms_deform_attn.py",
+    # the rest of the SOC model, for the whole-model training step of BASELINE.json configs[2] (tools/soc_step.py)
+    "utils.py",
+    "configs/a2d_sentences.yaml",
+    "models/soc.py",
+    "models/backbone.py",
+    "models/video_swin_transformer.py",
+    "models/position_encoding.py",
+    "models/vla.py",
+    "models/voc.py",
+    "models/segmentation.py",
+    "models/criterion.py",
+    "models/matcher.py",
+    "models/postprocessing.py",
 ]
 
 
