@@ -4,7 +4,11 @@ Frames are dealt out contiguously to the ranks (neurips2023_soc_b200.frames), ev
 communication, and the per-frame decoder states are gathered once at the end over NCCL -- the reference instead
 gives whole videos to processes (/root/reference/infer_refytb.py:92-109) and never shards one video.
 
-With --graph the rank's whole forward is captured in a CUDA graph and replayed (the op never synchronises).
+By default the transformer IS the reference's: DeformableTransformer of the unmodified models/deformable_transformer.py
+staged under baseline/_ref/soc (tools/stage_reference.py) -- 3 encoder + 3 decoder layers, 5 queries per frame, its own
+MSDeformAttn module and autograd function on this repo's two extension entry points.  --restated (or nothing staged)
+uses the small restatement below.  With --graph (restated model only: the reference's forward reads the level shapes
+on the host) the rank's whole forward is captured in a CUDA graph and replayed (the op never synchronises).
 
     python tools/inference_bench.py [--graph] [--amp]
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/inference_bench.py --amp
@@ -58,8 +62,23 @@ class Model(nn.Module):
         return tgt
 
 
+def reference_transformer(queries):
+    """DeformableTransformer of the staged, unmodified reference file (None when nothing is staged)."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.join(root, "baseline", "_ref", "soc")
+    if not os.path.exists(os.path.join(staged, "MANIFEST.json")):
+        return None
+    sys.path.insert(1, staged)                 # behind the repo root: MultiScaleDeformableAttention is this repo's shim
+    dt = importlib.import_module("models.deformable_transformer")
+    return dt.DeformableTransformer(d_model=256, nhead=8, num_encoder_layers=3, num_decoder_layers=3, dim_feedforward=2048,
+                                    dropout=0.0, activation="relu", return_intermediate_dec=True, num_feature_levels=4,
+                                    dec_n_points=4, enc_n_points=4)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--restated", action="store_true", help="the small restatement instead of the staged reference transformer")
     ap.add_argument("--frames", type=int, default=36)
     ap.add_argument("--queries", type=int, default=5)
     ap.add_argument("--steps", type=int, default=20)
@@ -86,15 +105,26 @@ def main():
     dec_ref = torch.rand(a.frames, a.queries, 1, 2, generator=g)[lo:hi].to(dev).expand(n, a.queries, L, 2).contiguous()
     enc_ref = pyramid_reference_points(shapes_l).to(dev)[None, :, None, :].expand(n, S, L, 2).contiguous()
     torch.manual_seed(0)
-    model = Model().to(dev).eval()
+    ref_model = None if (a.restated or a.graph) else reference_transformer(a.queries)
+    which = "reference DeformableTransformer (staged, unmodified)" if ref_model is not None else "restated layers"
+    model = (ref_model if ref_model is not None else Model()).to(dev).eval()
     with torch.no_grad():
         for m in model.modules():
-            if isinstance(m, MSDeformAttn):
+            if hasattr(m, "sampling_offsets") and hasattr(m, "attention_weights"):
                 m.sampling_offsets.weight.normal_(0, 0.02)
                 m.attention_weights.weight.normal_(0, 0.02)
+    if ref_model is not None:      # the reference's calling convention: per-level maps, masks, positions; tgt [b, t, q, c]
+        srcs = [src[:, s0:s0 + h * w].transpose(1, 2).reshape(n, 256, h, w).contiguous()
+                for (h, w), s0 in zip(shapes_l, level_start_index(shapes_l))]
+        poses = [pos[:, s0:s0 + h * w].transpose(1, 2).reshape(n, 256, h, w).contiguous()
+                 for (h, w), s0 in zip(shapes_l, level_start_index(shapes_l))]
+        masks = [torch.zeros(n, h, w, dtype=torch.bool, device=dev) for h, w in shapes_l]
+        query_embed = qpos[0].contiguous()
 
     def fwd():
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
+            if ref_model is not None:
+                return model(srcs, tgt[None], masks, poses, query_embed)[0][-1]      # last decoder layer: [frames, q, c]
             return model(src, pos, enc_ref, tgt, qpos, dec_ref, shapes, lsi)
 
     for _ in range(3):
@@ -127,6 +157,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"what": "36-frame video: 3 encoder + 3 decoder layers, forward, frames sharded, output gathered",
+                          "model": which,
                           "frames": a.frames, "queries_per_frame": a.queries, "n_gpus": world, "amp_bf16": a.amp,
                           "cuda_graph": a.graph, "ms_per_video": float(ms.item()),
                           "frames_per_s": a.frames / (float(ms.item()) * 1e-3),
