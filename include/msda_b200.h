@@ -189,6 +189,27 @@ int msda_last_launch_count(void);
 void msda_profile_enable(int on);
 int msda_profile_read(char *names, size_t names_cap, float *ms, int cap);
 
+/* ---- the memory-bound glue of the encoder layer around the op ------------------------------
+ * The reference layer does  src = norm(src + branch)  twice per layer as separate PyTorch kernels
+ * (/root/reference/models/deformable_transformer.py:253-263 and :247-251: add, nn.LayerNorm; in the backward the
+ * LayerNorm input gradient, two parameter-gradient reductions and the add of the residual branch).  These two entry
+ * points do each direction in one pass over the rows; they have no counterpart in the reference's FFI (it calls
+ * ATen), the host side is neurips2023_soc_b200/modules/encoder_layer.py.
+ *   out    = LayerNorm(branch + residual) * gamma + beta                 [rows][channels], dtype F32 or BF16
+ *   presum = branch + residual (rounded to dtype; may alias `branch`)      kept for the backward
+ *   mean, rstd                                                             [rows] fp32
+ * backward: grad_in (the gradient of BOTH branch and residual), grad_gamma / grad_beta [channels] fp32, summed in a
+ * fixed order (deterministic) through `workspace` (msda_add_layernorm_backward_workspace_bytes).
+ * channels must be 256 (d_model of every SOC config); anything else returns MSDA_ERR_UNSUPPORTED. */
+int msda_add_layernorm_forward(const void *branch, const void *residual, const float *gamma, const float *beta,
+                               void *out, void *presum, float *mean, float *rstd,
+                               long long rows, int channels, int dtype, float eps, void *cuda_stream);
+size_t msda_add_layernorm_backward_workspace_bytes(long long rows, int channels);
+int msda_add_layernorm_backward(const void *grad_out, const void *presum, const float *mean, const float *rstd,
+                                const float *gamma, void *grad_in, float *grad_gamma, float *grad_beta,
+                                void *workspace, size_t workspace_bytes,
+                                long long rows, int channels, int dtype, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

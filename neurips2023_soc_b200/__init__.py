@@ -6,6 +6,8 @@ One hot path, behind the reference's own operator boundary:
   ``ms_deform_attn_backward`` with the reference extension's signatures;
 * ``functions.MSDeformAttnFunction`` -- the autograd function;
 * ``modules.MSDeformAttn`` -- the ``nn.Module`` (same parameters and state-dict keys);
+* ``modules.DeformableTransformerEncoderLayer`` / ``DeformableTransformerEncoder`` -- the op's caller in the encoder
+  with the elementwise glue fused around it (SURVEY.md 8f-2), same constructor, parameters and forward signatures;
 * ``frames`` -- frame sharding of a batch over the ranks of one node.
 
 The kernels live in ``csrc/`` and are reached through the C ABI in ``include/msda_b200.h``
@@ -13,7 +15,8 @@ The kernels live in ``csrc/`` and are reached through the C ABI in ``include/msd
 tensors, calls raise.
 """
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
-from .modules import MSDeformAttn
+from .modules import DeformableTransformerEncoder, DeformableTransformerEncoderLayer, MSDeformAttn
 
-__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MSDeformAttn"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MSDeformAttn", "DeformableTransformerEncoderLayer",
+           "DeformableTransformerEncoder"]
 __version__ = "0.1.0"

@@ -242,3 +242,53 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
 
 def last_launch_count() -> int:
     return int(_lib.load().msda_last_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+# residual add + LayerNorm in one pass each way (msda_add_layernorm_*, include/msda_b200.h)
+def add_layernorm_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.shape[-1] == 256 and x.dtype in (torch.float32, torch.bfloat16)
+
+
+def add_layernorm_forward(branch: torch.Tensor, residual: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                          eps: float = 1e-5):
+    """``LayerNorm(branch + residual) * gamma + beta`` over the last dim (256 channels).  Returns
+    ``(out, presum, mean, rstd)``; ``presum`` (= branch + residual, what the backward needs) is written over
+    ``branch``, which the caller must no longer use."""
+    _check_inputs([("branch", branch), ("residual", residual), ("gamma", gamma), ("beta", beta)])
+    _require(branch.shape == residual.shape and branch.dtype == residual.dtype, "branch and residual must match")
+    _require(gamma.dtype == torch.float32 and beta.dtype == torch.float32 and gamma.numel() == branch.shape[-1]
+             and beta.numel() == branch.shape[-1], "gamma / beta must be fp32 vectors of the channel count")
+    _require(branch.dtype in _DTYPE, f"unsupported dtype {branch.dtype}")
+    C = branch.shape[-1]
+    rows = branch.numel() // C
+    lib = _lib.load()
+    with torch.cuda.device(branch.device):
+        out = torch.empty_like(branch)
+        mean = torch.empty(rows, dtype=torch.float32, device=branch.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=branch.device)
+        _lib.check(lib.msda_add_layernorm_forward(
+            branch.data_ptr(), residual.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), branch.data_ptr(),
+            mean.data_ptr(), rstd.data_ptr(), rows, C, _DTYPE[branch.dtype], float(eps), torch.cuda.current_stream().cuda_stream))
+    return out, branch, mean, rstd
+
+
+def add_layernorm_backward(grad_out: torch.Tensor, presum: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                           gamma: torch.Tensor):
+    """-> ``(grad_in, grad_gamma, grad_beta)``; ``grad_in`` is the gradient of both the branch and the residual."""
+    _check_inputs([("grad_out", grad_out), ("presum", presum), ("mean", mean), ("rstd", rstd), ("gamma", gamma)])
+    _require(grad_out.shape == presum.shape and grad_out.dtype == presum.dtype, "grad_out and presum must match")
+    C = presum.shape[-1]
+    rows = presum.numel() // C
+    lib = _lib.load()
+    with torch.cuda.device(presum.device):
+        grad_in = torch.empty_like(presum)
+        grad_gamma = torch.empty(C, dtype=torch.float32, device=presum.device)
+        grad_beta = torch.empty(C, dtype=torch.float32, device=presum.device)
+        ws_bytes = int(lib.msda_add_layernorm_backward_workspace_bytes(rows, C))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=presum.device)
+        _lib.check(lib.msda_add_layernorm_backward(
+            grad_out.data_ptr(), presum.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), grad_in.data_ptr(),
+            grad_gamma.data_ptr(), grad_beta.data_ptr(), ws.data_ptr(), ws_bytes, rows, C, _DTYPE[presum.dtype],
+            torch.cuda.current_stream().cuda_stream))
+    return grad_in, grad_gamma, grad_beta

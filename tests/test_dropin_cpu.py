@@ -131,3 +131,36 @@ def test_unmodified_deformable_transformer_runs_on_this_module(reference_namespa
     hs.sum().backward()                                     # backward goes through ms_deform_attn_backward
     assert all(p.grad is not None and torch.isfinite(p.grad).all()
                for n, p in model.named_parameters() if "sampling_offsets" in n)
+
+
+def test_encoder_layer_mirrors_reference_layer(reference_namespace, oracle_backed):
+    """this repo's DeformableTransformerEncoderLayer / Encoder carry the reference's parameter names and
+    forward signatures (deformable_transformer.py:225-293), load its state dict and -- on the op-by-op path, which is
+    what CPU tensors take -- reproduce its outputs."""
+    from neurips2023_soc_b200 import DeformableTransformerEncoder, DeformableTransformerEncoderLayer
+    ops = types.ModuleType("models.ops")
+    ops.__path__ = []
+    mods = types.ModuleType("models.ops.modules")
+    mods.MSDeformAttn = MSDeformAttn
+    sys.modules["models.ops"] = ops
+    sys.modules["models.ops.modules"] = mods
+    dt = importlib.import_module("models.deformable_transformer")
+    torch.manual_seed(0)
+    theirs = dt.DeformableTransformerEncoder(dt.DeformableTransformerEncoderLayer(256, 64, 0.0, "relu", 2, 8, 4), 2)
+    ours = DeformableTransformerEncoder(DeformableTransformerEncoderLayer(256, 64, 0.0, "relu", 2, 8, 4), 2)
+    assert sorted(theirs.state_dict().keys()) == sorted(ours.state_dict().keys())
+    with torch.no_grad():
+        for p in theirs.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    ours.load_state_dict(theirs.state_dict())
+    shapes = torch.tensor([(4, 6), (2, 3)])
+    lsi = torch.tensor([0, 24])
+    src, pos = torch.randn(2, 30, 256), torch.randn(2, 30, 256)
+    ratios = torch.rand(2, 2, 2) * 0.3 + 0.7
+    mask = torch.zeros(2, 30, dtype=torch.bool)
+    mask[0, -4:] = True
+    assert torch.allclose(ours.get_reference_points(shapes, ratios, "cpu"), theirs.get_reference_points(shapes, ratios, "cpu"))
+    with torch.no_grad():
+        a = ours(src, shapes, lsi, ratios, pos, mask)
+        b = theirs(src, shapes, lsi, ratios, pos, mask)
+    assert torch.allclose(a, b, atol=1e-5), (a - b).abs().max()

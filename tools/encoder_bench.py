@@ -76,7 +76,10 @@ def reference_encoder(layers, keep_reference_module):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--restated", action="store_true", help="the small restatement of the encoder instead of the staged reference class")
+    ap.add_argument("--b200-layers", action="store_true",
+                    help="this repo's DeformableTransformerEncoder of fused layers (bf16 end to end, SURVEY.md 8f-2)")
     ap.add_argument("--reference-module", action="store_true", help="keep the reference's own MSDeformAttn module / autograd function too")
+    ap.add_argument("--graph", action="store_true", help="capture the whole training step (forward, backward, AdamW) in a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="print the step's CUDA kernels by total time (torch.profiler)")
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16)
@@ -98,9 +101,15 @@ def main():
     ref = pyramid_reference_points(shapes_l).to(dev)[None, :, None, :].expand(a.frames, S, len(shapes_l), 2).contiguous()
     src = torch.randn(a.frames, S, 256, device=dev)
     pos = torch.randn(a.frames, S, 256, device=dev)
-    model = None if a.restated else reference_encoder(a.layers, a.reference_module)
+    model = None if (a.restated or a.b200_layers) else reference_encoder(a.layers, a.reference_module)
     which = "reference DeformableTransformerEncoder (staged, unmodified)" + (" + reference MSDeformAttn module" if a.reference_module else "")
-    if model is None:
+    if a.b200_layers:
+        from neurips2023_soc_b200 import DeformableTransformerEncoder, DeformableTransformerEncoderLayer
+        model = DeformableTransformerEncoder(DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4), a.layers)
+        which = "neurips2023_soc_b200.DeformableTransformerEncoder (fused layers, bf16 end to end)"
+        ratios = torch.ones(a.frames, len(shapes_l), 2, device=dev)
+        call = lambda net: net(src, shapes, lsi, ratios, pos, None)                           # noqa: E731
+    elif model is None:
         model, which = Encoder(a.layers), "restated encoder"
         call = lambda net: net(src, pos, ref, shapes, lsi)                                    # noqa: E731
     else:
@@ -115,9 +124,9 @@ def main():
                 m.sampling_offsets.weight.normal_(0, 0.02)
                 m.attention_weights.weight.normal_(0, 0.02)
     net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, capturable=a.graph)
 
-    def step():
+    def eager_step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=a.amp):
             out = call(net)
@@ -125,6 +134,26 @@ def main():
         loss.backward()
         opt.step()
         return loss
+
+    step = eager_step
+    if a.graph:
+        # whole-step capture (torch's recipe): warm up on a side stream, then record forward, backward and the
+        # optimizer step once; the op never synchronises and every buffer it allocates comes from the graph's pool
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = eager_step()
+
+        def step():
+            graph.replay()
+            return static_loss
 
     for _ in range(3):
         step()
@@ -155,7 +184,7 @@ def main():
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
     if rank == 0:
         print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "encoder": which, "layers": a.layers, "frames_per_gpu": a.frames,
-                          "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "n_gpus": world, "ms_per_step": float(ms.item()),
+                          "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "cuda_graph": a.graph, "n_gpus": world, "ms_per_step": float(ms.item()),
                           "queries_per_s": world * a.frames * S / (float(ms.item()) * 1e-3),
                           "msda_kernels_ms_per_step": fwd_ms, "loss": float(loss)}))
     if world > 1:
