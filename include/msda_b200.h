@@ -158,6 +158,20 @@ int msda_backward_fused(const void *value, const int64_t *spatial_shapes, const 
                         int N, int S, int M, int D, int L, int Lq, int P,
                         int value_dtype, int aux_dtype, int im2col_step, void *cuda_stream, unsigned flags);
 
+/* The same without ever materialising sampling_loc / attn_weight (the encoder drops them:
+ * /root/reference/models/deformable_transformer.py:255 keeps only the first of the module's three results).
+ * msda_forward_fused accepts NULL for BOTH sampling_loc_out and attn_weight_out; this backward then takes what that
+ * forward took -- reference_points, the raw sampling_offsets and attn_logits (in_dtype) -- recomputes the prologue in
+ * its staging threads and writes grad_sampling_offsets / grad_attn_logits in in_dtype (bf16 under a bf16 layer: no
+ * fp32 round trip of 384 values per query).  Needs the index the forward left (index != NULL); only for calls that
+ * keep one (msda_index_bytes != 0). */
+int msda_backward_fused_raw(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                            const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attn_logits,
+                            void *workspace, size_t workspace_bytes, void *index, size_t index_bytes,
+                            int N, int S, int M, int D, int L, int Lq, int P,
+                            int value_dtype, int in_dtype, int im2col_step, void *cuda_stream, unsigned flags);
+
 /* Bytes of device scratch msda_backward needs for this problem size. */
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P,
                                      int value_dtype, int aux_dtype);

@@ -21,7 +21,7 @@ EXPORTS = (
     "msda_backward_workspace_bytes", "msda_backward", "msda_backward_ex", "msda_last_launch_count",
     "msda_profile_enable", "msda_profile_read",
     "msda_index_bytes", "msda_forward_indexed", "msda_backward_indexed", "msda_forward_fused", "msda_backward_fused",
-    "msda_add_layernorm_forward", "msda_add_layernorm_backward", "msda_add_layernorm_backward_workspace_bytes",
+    "msda_backward_fused_raw", "msda_add_layernorm_forward", "msda_add_layernorm_backward", "msda_add_layernorm_backward_workspace_bytes",
 )
 
 _lib = None
@@ -65,6 +65,8 @@ def load() -> ctypes.CDLL:
     lib.msda_backward_indexed.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     lib.msda_backward_fused.restype = i
     lib.msda_backward_fused.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
+    lib.msda_backward_fused_raw.restype = i
+    lib.msda_backward_fused_raw.argtypes = [vp] * 11 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     ll, fl, fp = ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
     lib.msda_add_layernorm_forward.restype = i
     lib.msda_add_layernorm_forward.argtypes = [vp] * 8 + [ll, i, i, fl, vp]

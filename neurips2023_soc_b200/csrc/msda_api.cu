@@ -207,9 +207,9 @@ int launch_fwd_tile_rowb(const Params& p, cudaStream_t st) {
     const int rounds = rounds_for(G, p.Lq);
     const int tile_q = (kThreads / G) * rounds;
     const long long tiles = (long long)p.N * p.M * ceil_div(p.Lq, tile_q) * 2;  // pyramid tiling may need more passes
-    const char* name = p.loc_out ? "msda_fwd_tile_kernel<fused>" : "msda_fwd_tile_kernel";
+    const char* name = p.ref ? "msda_fwd_tile_kernel<fused>" : "msda_fwd_tile_kernel";
     prof_begin(st, name);
-    if (p.loc_out) {   // fused prologue: softmax + sampling locations computed in the staging threads
+    if (p.ref) {   // fused prologue: softmax + sampling locations computed in the staging threads
         if (p.bin_off) {
             auto k = msda_fwd_tile_kernel<T, TA, VEC, G, P, true, true, ROWB>;
             k<<<persistent_grid(k, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
@@ -270,6 +270,14 @@ int launch_bwd_sample_tile_rowb(const Params& p, cudaStream_t st) {
             MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<atomic>");
             return MSDA_OK;
         }
+    }
+    if ((p.flags & kFlagChain) && p.ref != nullptr) {      // raw offsets / logits in, prologue recomputed in the staging threads
+        auto kr = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false, ROWB, true, true>;
+        prof_begin(st, "msda_bwd_sample_tile_kernel<chain,raw>");
+        kr<<<persistent_grid(kr, kThreads, tiles), kThreads, 0, st>>>(p, rounds);
+        prof_end(st);
+        MSDA_LAUNCHED("msda_bwd_sample_tile_kernel<chain,raw>");
+        return MSDA_OK;
     }
     if (p.flags & kFlagChain) {
         auto kc = msda_bwd_sample_tile_kernel<T, TA, VEC, G, P, true, false, ROWB, true>;
@@ -647,7 +655,8 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
     msda_host::g_launches.store(0);
     const bool fused = reference_points != nullptr;
     if (fused) {   // the raw offsets / logits may be bf16 next to fp32 values only through the value dtype rule below
-        if (!loc_out || !attn_out) return fail(MSDA_ERR_INVALID_ARGUMENT, "null sampling_loc / attn_weight output");
+        if ((loc_out == nullptr) != (attn_out == nullptr))
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "sampling_loc / attn_weight outputs: pass both or neither");
         if (L * P > kSC)
             return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue needs L*P <= %d, got %d", kSC, L * P);
     }
@@ -687,7 +696,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
 
     const bool aux32 = aux_dtype == MSDA_F32;
     const bool tile = pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16);
-    if (fused && !(tile && aligned16(reference_points) && aligned16(loc_out) && aligned16(attn_out)))
+    if (fused && !(tile && aligned16(reference_points) && aligned16(loc_out) && aligned16(attn_out)))   /* null is aligned */
         return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue exists for the tile kernels only (fp32/bf16, D and P as in DESIGN.md)");
     switch (value_dtype) {
         case MSDA_F32:
@@ -765,7 +774,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
-                         unsigned flags, bool chain) {
+                         unsigned flags, bool chain, const void* reference_points = nullptr) {
     msda_host::g_launches.store(0);
     flags &= ~kFlagChain;
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
@@ -798,6 +807,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
     p.value = value; p.shapes = spatial_shapes; p.lsi = level_start_index;
     p.loc = sampling_loc; p.attn = attn_weight; p.grad_out = grad_output;
     p.grad_value = grad_value; p.grad_loc = grad_sampling_loc; p.grad_attn = grad_attn_weight;
+    p.ref = static_cast<const float*>(reference_points);     // raw-input chain variant only
     p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = LP;
     p.id_shift = shift;
     p.sb_max = w.sb_max; p.big_cap = w.big_cap;
@@ -858,6 +868,23 @@ int msda_backward_fused(const void* value, const int64_t* spatial_shapes, const 
     return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
                          grad_sampling_offsets, grad_attn_logits, workspace, workspace_bytes, index, index_size, N, S, M,
                          D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags, true);
+}
+
+int msda_backward_fused_raw(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const void* reference_points, const void* sampling_offsets, const void* attn_logits,
+                            const void* grad_output, void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
+                            void* workspace, size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M,
+                            int D, int L, int Lq, int P, int value_dtype, int in_dtype, int im2col_step, void* cuda_stream,
+                            unsigned flags) {
+    if (!reference_points) return fail(MSDA_ERR_INVALID_ARGUMENT, "null reference_points");
+    if (!aligned16(reference_points)) return fail(MSDA_ERR_INVALID_ARGUMENT, "reference_points must be 16-byte aligned");
+    if (direct_call(S, Lq, P, flags) || msda_index_bytes(N, S, M, D, L, Lq, P) == 0)
+        return fail(MSDA_ERR_UNSUPPORTED, "msda_backward_fused_raw is for calls that keep the inverse index (many queries per frame)");
+    if (!index)      // a backward that counts for itself would have to locate the samples from tensors that were never written
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_fused_raw needs the index the matching msda_forward_fused left");
+    return backward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, grad_output, grad_value,
+                         grad_sampling_offsets, grad_attn_logits, workspace, workspace_bytes, index, index_size, N, S, M, D,
+                         L, Lq, P, value_dtype, in_dtype, im2col_step, cuda_stream, flags, true, reference_points);
 }
 
 int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

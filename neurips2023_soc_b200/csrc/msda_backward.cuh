@@ -82,18 +82,24 @@ __device__ __forceinline__ void reduce_scatter(float* v, const int gl) {
 // applied on the way out: grad_loc / grad_attn then hold the gradients of the RAW sampling offsets and attention
 // logits --  d/d offset = grad_loc / (W, H) = a * (dX, dY);  d/d logit_s = a_s * (g_s - sum_t a_t g_t)  (softmax) --
 // for calls whose L*P samples are one chunk (the fused prologue's own restriction).
-template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC, int ROWB = 0, bool CHAIN = false>
+// RAWIN (with CHAIN): `loc` / `attn` are the RAW sampling offsets / attention logits and p.ref the reference points: the
+// prologue is recomputed in the staging threads exactly as the fused forward does (msda_tiles.cuh: fused_prologue), so
+// that neither the sampling locations nor the attention weights are ever materialised (msda_backward_fused_raw).
+template <typename T, typename TA, int VEC, int G, int P, bool FILL, bool ATOMIC, int ROWB = 0, bool CHAIN = false, bool RAWIN = false>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample_tile_kernel(const Params p, const int rounds) {
     using TS = TileShape<G>;
     constexpr int NG = TS::NG;
     constexpr int LPC = (P >= kSC) ? 1 : kSC / P;
     constexpr int PPC = (P >= kSC) ? kSC : P;
     static_assert(!ATOMIC || (VEC == 4 && sizeof(T) == 4), "atomic arm is fp32 only");
+    static_assert(!RAWIN || CHAIN, "the raw-input variant always applies the chain rule");
 
     __shared__ Level lv[kMaxLevels];
     __shared__ TileMap tm;
     __shared__ int s_sb, s_sq;
     __shared__ uint4 desc[2][NG * kDescStride];
+    // CHAIN: d/d weight of this lane's samples, kept unrounded until the (query, head)'s softmax sum is known
+    __shared__ float s_ga[CHAIN ? 4 : 1][CHAIN ? kThreads : 1];      // (level step, sample of the lane): at most 4 per lane
 
     const int tile_q = NG * rounds;
     load_levels(p, lv, &s_sb, &s_sq);
@@ -114,8 +120,8 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
     if (cur.t >= total_tiles) return;
     Tile tl = decode_tile(p, lv, &tm, cur.t, tile_q);
     Staged<TS::DPT> st;
-    stage_load<TA, G, P>(st, p, &tm, tl, cur, loc, attn);
-    stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, tl, cur, desc[0], index_usable(p, s_sb));
+    stage_load<TA, G, P, RAWIN>(st, p, &tm, tl, cur, loc, attn);
+    stage_build<G, P, (FILL ? kIndexFill : kIndexNone), RAWIN, CHAIN>(st, p, lv, tl, cur, desc[0], index_usable(p, s_sb));
     __syncthreads();
 
     int buf = 0;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         Tile ntl = tl;
         if (has_next) {
             if (nxt.t != cur.t) ntl = decode_tile(p, lv, &tm, nxt.t, tile_q);
-            stage_load<TA, G, P>(st, p, &tm, ntl, nxt, loc, attn);
+            stage_load<TA, G, P, RAWIN>(st, p, &tm, ntl, nxt, loc, attn);
         }
 
         const int q_mine = tile_query(p, &tm, tl, cur.r * NG + grp);
@@ -278,11 +284,13 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                 const int sgo = cur.c0 + sbase + s;
                 if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
                     const size_t si = qm_mine * p.LP + sgo;
-                    gattn[si] = Elem<TA>::from_f(ga);
                     if constexpr (CHAIN) {
+                        static_assert(LPC * SPL <= 4, "a lane finishes at most four samples per chunk");
+                        s_ga[lc * SPL + i][threadIdx.x] = ga;
                         store_xy(gloc + 2 * si, a * gx, a * gy);
                         chain_dot = fmaf(a, ga, chain_dot);
                     } else {
+                        gattn[si] = Elem<TA>::from_f(ga);
                         store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
                     }
                 }
@@ -304,16 +312,16 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
                     const int sgo = cur.c0 + sbase + s;
                     if (q_mine >= 0 && ((gl * CPL) & 3) == 0 && sgo < p.LP) {
                         const size_t si = qm_mine * p.LP + sgo;
-                        // the weight comes from the tensor, not the descriptor: a rejected sample's descriptor is all
-                        // zero, yet its logit still takes  -a_s * sum_t a_t g_t
-                        const float a = (float)Elem<TA>::to_f(attn[si]);
-                        gattn[si] = Elem<TA>::from_f(a * ((float)Elem<TA>::to_f(gattn[si]) - chain_dot));
+                        // the descriptor keeps the weight of rejected samples too (stage_build<KEEPW>): their logits
+                        // still take  -a_s * sum_t a_t g_t
+                        const float a = __uint_as_float(drow[sbase + s].w);
+                        gattn[si] = Elem<TA>::from_f(a * (s_ga[lc * SPL + i][threadIdx.x] - chain_dot));
                     }
                 }
             }
         }
 
-        if (has_next) stage_build<G, P, (FILL ? kIndexFill : kIndexNone)>(st, p, lv, ntl, nxt, desc[buf ^ 1], index_usable(p, s_sb));
+        if (has_next) stage_build<G, P, (FILL ? kIndexFill : kIndexNone), RAWIN, CHAIN>(st, p, lv, ntl, nxt, desc[buf ^ 1], index_usable(p, s_sb));
         __syncthreads();
         if (!has_next) break;
         cur = nxt;

@@ -110,9 +110,11 @@ __device__ __forceinline__ void fused_prologue(Staged<TileShape<G>::DPT>& st, co
             st.a[k] = e / sum;
             st.x[k] = st.rx[k] + st.x[k] / (float)L_.W;
             st.y[k] = st.ry[k] + st.y[k] / (float)L_.H;
-            const size_t si = (((size_t)tl.n * p.Lq + st.q[k]) * p.M + tl.m) * p.LP + sg;
-            reinterpret_cast<float2*>(p.loc_out)[si] = make_float2(st.x[k], st.y[k]);
-            p.attn_out[si] = st.a[k];
+            if (p.loc_out != nullptr) {      // null: the caller keeps only the raw projections (msda_backward_fused_raw)
+                const size_t si = (((size_t)tl.n * p.Lq + st.q[k]) * p.M + tl.m) * p.LP + sg;
+                reinterpret_cast<float2*>(p.loc_out)[si] = make_float2(st.x[k], st.y[k]);
+                p.attn_out[si] = st.a[k];
+            }
         }
     }
 }
@@ -129,7 +131,9 @@ __device__ __forceinline__ void fused_prologue(Staged<TileShape<G>::DPT>& st, co
 // floating-point result.
 constexpr int kIndexNone = 0, kIndexCount = 1, kIndexFill = 2;
 
-template <int G, int P, int MODE, bool FUSED = false>
+// KEEPW: a rejected sample's descriptor keeps its attention weight in .w (no corner bit set, so nothing is loaded
+// for it): the in-kernel softmax backward needs the weight of every sample, accepted or not.
+template <int G, int P, int MODE, bool FUSED = false, bool KEEPW = false>
 __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const Params& p, const Level* lv,
                                             const Tile& tl, const Work& w, uint4* __restrict__ desc,
                                             const bool index_ok = true) {
@@ -159,6 +163,7 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
         slot[k] = 0u;
         if (st.q[k] >= 0) {
             const Sample<float> s = locate(st.x[k], st.y[k], L_.H, L_.W);
+            if constexpr (KEEPW) d.w = __float_as_uint(st.a[k]);
             if (s.ok) {
                 const unsigned h0 = s.h_lo >= 0, w0 = s.w_lo >= 0;
                 const unsigned h1 = s.h_lo + 1 <= L_.H - 1, w1 = s.w_lo + 1 <= L_.W - 1;

@@ -70,8 +70,13 @@ class _EncoderLayerFunction(Function):
         if pad is not None:
             value = value.masked_fill(pad[..., None], 0.0)
         value = value.view(N, S, M, C // M)
+        # the encoder never looks at the sampling locations / attention weights: they are not written at all when the
+        # call keeps an inverse index (many queries per frame), the backward then recomputes them from the raw projections
+        raw = msda_ext.forward_index_bytes(value, off) > 0
         attn_out, loc, attn, index = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64,
-                                                                           want_index=True)
+                                                                           want_index=True, materialize=not raw)
+        if raw:
+            loc, attn = off, logit
         a = F.linear(attn_out.view(T, C), Wo_, cast(bo))
         x1, s1, mean1, rstd1 = msda_ext.add_layernorm_forward(a, x2, g1, be1, eps1)       # s1 overwrites a
         h = torch._addmm_activation(cast(b1), x1, W1_.t())                                 # relu(x1 W1^T + b1), one GEMM
@@ -79,7 +84,7 @@ class _EncoderLayerFunction(Function):
         out, s2, mean2, rstd2 = msda_ext.add_layernorm_forward(y, x1, g2, be2, eps2)       # s2 overwrites y
         ctx.save_for_backward(x2, q2, value, loc, attn, attn_out, s1, mean1, rstd1, x1, h, s2, mean2, rstd2,
                               shapes, lsi, Wso_, Waw_, Wv_, Wo_, W1_, W2_, g1, g2)
-        ctx.index, ctx.pad = index, pad
+        ctx.index, ctx.pad, ctx.raw, ctx.ref = index, pad, raw, (ref if raw else None)
         ctx.has_pos = pos is not None
         ctx.dims = (N, S, C, M, L, P)
         return out.view(N, S, C)
@@ -110,7 +115,11 @@ class _EncoderLayerFunction(Function):
         dbo = _colsum(dz1)
         dao = torch.mm(dz1, Wo_).view(N, S, C)
         index, ctx.index = ctx.index, None
-        dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc, attn, dao, 64, index=index)
+        if ctx.raw:      # loc / attn hold the raw offsets / logits
+            dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ctx.ref, loc, attn, dao, 64,
+                                                                               index=index)
+        else:
+            dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc, attn, dao, 64, index=index)
         if ctx.pad is not None:
             dvalue = dvalue.view(N, S, C).masked_fill(ctx.pad[..., None], 0.0)
         dv2 = dvalue.reshape(T, C)

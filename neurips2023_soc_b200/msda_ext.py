@@ -193,6 +193,42 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, samp
     return [grad_value, grad_off, grad_logits]
 
 
+def ms_deform_attn_backward_fused_raw(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                      attn_logits, grad_output, im2col_step: int, index, flags: int | None = None
+                                      ) -> List[torch.Tensor]:
+    """Backward of ``ms_deform_attn_forward_fused(..., materialize=False)`` (msda_backward_fused_raw): takes what that
+    forward took plus its index, returns ``[grad_value, grad_sampling_offsets, grad_attention_logits]`` in the dtypes
+    of value / the raw projections."""
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
+                   ("attn_logits", attn_logits), ("grad_output", grad_output)])
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_offsets.shape
+    dims = (N, S, M, D, L, Lq, P)
+    _require(tuple(reference_points.shape) == (N, Lq, L, 2) and reference_points.dtype == torch.float32,
+             "reference_points must be fp32 (N, Lq, L, 2)")
+    _require(sampling_offsets.dtype == attn_logits.dtype and sampling_offsets.dtype in (value.dtype, torch.float32),
+             "sampling_offsets / attn_logits must share a dtype: the value dtype or float32")
+    _require(grad_output.dtype == value.dtype and grad_output.numel() == N * Lq * M * D,
+             "grad_output must be (N, Lq, M*D) in the dtype of value")
+    _require(index is not None, "the index of the matching forward is required")
+    lib = _lib.load()
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attn_logits)
+        vdt, adt = _DTYPE[value.dtype], _DTYPE[sampling_offsets.dtype]
+        ws_bytes = int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
+        _lib.check(lib.msda_backward_fused_raw(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+            grad_off.data_ptr(), grad_logits.data_ptr(), ws.data_ptr(), ws_bytes, index.data_ptr(), index.numel(),
+            *dims, vdt, adt, int(im2col_step), torch.cuda.current_stream().cuda_stream,
+            DEFAULT_FLAGS if flags is None else flags))
+    return [grad_value, grad_off, grad_logits]
+
+
 def fused_prologue_supported(value, n_levels: int, n_points: int, ref_dim: int) -> bool:
     """Whether ms_deform_attn_forward_fused has a kernel for this call: tile-kernel
     shapes (fp32 rows of 64/128/256 B, bf16 rows of 64/128/256 B, P in {4, 8}), L*P <= 16, 2-d reference
@@ -204,9 +240,11 @@ def fused_prologue_supported(value, n_levels: int, n_points: int, ref_dim: int) 
 
 
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                                 attn_logits, im2col_step: int, flags: int | None = None, want_index: bool = False):
+                                 attn_logits, im2col_step: int, flags: int | None = None, want_index: bool = False,
+                                 materialize: bool = True):
     """Forward with the module's prologue fused in (msda_forward_fused): returns
-    ``(output, sampling_locations fp32, attention_weights fp32[, index])``."""
+    ``(output, sampling_locations fp32, attention_weights fp32[, index])``.  ``materialize=False``: the two middle
+    results are never written (returned as None); the matching backward is ``ms_deform_attn_backward_fused_raw``."""
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
                    ("attn_logits", attn_logits)])
@@ -224,8 +262,8 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
     lib = _lib.load()
     with torch.cuda.device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-        loc = torch.empty((N, Lq, M, L, P, 2), dtype=torch.float32, device=value.device)
-        attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device)
+        loc = torch.empty((N, Lq, M, L, P, 2), dtype=torch.float32, device=value.device) if materialize else None
+        attn = torch.empty((N, Lq, M, L, P), dtype=torch.float32, device=value.device) if materialize else None
         index, index_ptr, index_bytes = None, None, 0
         if want_index:
             index_bytes = int(lib.msda_index_bytes(*dims))
@@ -234,7 +272,8 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
                 index_ptr = index.data_ptr()
         _lib.check(lib.msda_forward_fused(
             value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
-            sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+            sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(),
+            None if loc is None else loc.data_ptr(), None if attn is None else attn.data_ptr(),
             index_ptr, index_bytes, *dims, _DTYPE[value.dtype], _DTYPE[sampling_offsets.dtype], int(im2col_step),
             torch.cuda.current_stream().cuda_stream, DEFAULT_FLAGS if flags is None else flags))
     return (out, loc, attn, index) if want_index else (out, loc, attn)

@@ -177,3 +177,34 @@ def test_encoder_of_fused_layers_against_reference_encoder():
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "misc"]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_raw_fused_backward_matches_materialised_one(vdt, adt):
+    """msda_forward_fused without its two middle outputs + msda_backward_fused_raw against the materialising pair:
+    same output bits, same grad_value bits (the index entries carry the same values), gradients of the raw
+    projections equal up to the rounding of the dtype they are written in."""
+    g = torch.Generator().manual_seed(11)
+    shapes_l = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in shapes_l)
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    shapes = torch.tensor(shapes_l, dtype=torch.long, device=DEV)
+    lsi = torch.tensor(level_start_index(shapes_l), dtype=torch.long, device=DEV)
+    value = torch.randn(N, S, M, D, generator=g).to(DEV, vdt)
+    ref = DeformableTransformerEncoder.get_reference_points(shapes_l, torch.ones(N, L, 2, device=DEV), DEV).contiguous()
+    off = (torch.randn(N, S, M, L, P, 2, generator=g) * 3).to(DEV, adt)
+    logit = torch.randn(N, S, M, L * P, generator=g).to(DEV, adt)
+    go = torch.randn(N, S, M * D, generator=g).to(DEV, vdt)
+    out_a, loc, attn, idx_a = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64, want_index=True)
+    out_b, none1, none2, idx_b = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64, want_index=True,
+                                                                       materialize=False)
+    assert none1 is None and none2 is None and torch.equal(out_a, out_b) and torch.equal(idx_a, idx_b)
+    gv_a, goff_a, glog_a = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc, attn, go, 64, index=idx_a)
+    gv_b, goff_b, glog_b = msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ref, off, logit, go, 64, index=idx_b)
+    assert goff_b.dtype == adt and glog_b.dtype == adt
+    assert torch.equal(gv_a, gv_b)
+    tol = 1e-6 if adt == torch.float32 else 1e-2
+    assert _rel(goff_b, goff_a) <= tol and _rel(glog_b.view_as(glog_a), glog_a) <= tol
+    with pytest.raises(RuntimeError):          # a decoder-shaped call keeps no index: not this entry point
+        msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ref[:, :5].contiguous(), off[:, :5].contiguous(),
+                                                   logit[:, :5].contiguous(), go[:, :5].contiguous(), 64, index=idx_b)
