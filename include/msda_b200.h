@@ -83,6 +83,8 @@ enum msda_status {
 #define MSDA_FLAG_BIN_KERNEL 32u   /* A/B: grad_value through the one-kernel bin pass (msda_bwd_bin.cuh: entries sorted and
                                       summed in shared memory, half the index traffic) instead of rank-sort + row walker;
                                       measured slower on B200, kept for comparison */
+#define MSDA_FLAG_DIRECT_SPLIT 64u  /* A/B: decoder-shaped backward as memset + sample-gradient kernel + direct gather
+                                      (three launches) instead of the one kernel that does all three */
 #define MSDA_FLAG_WALK_DENSE 16u   /* force the inverse-index pipeline for grad_value even when the call is small enough
                                       for the direct shared-memory gather (decoder-shaped calls, Lq * P <= 512) */
 

@@ -15,6 +15,7 @@ F32, BF16, F16, F64 = 0, 1, 2, 3
 FLAG_PYRAMID_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC4 = 1, 2, 4, 8
 FLAG_WALK_DENSE = 16
 FLAG_BIN_KERNEL = 32
+FLAG_DIRECT_SPLIT = 64
 
 EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",

@@ -401,14 +401,29 @@ int ceil_log2(long long x) {
     return k;
 }
 
+constexpr unsigned kFlagDirectAll = 0x40000000u;   // internal: the direct kernel does the whole backward (see backward_typed)
+
 template <typename T, typename TA, int VEC, int G>
 int launch_grad_value_direct(const Params& p, cudaStream_t st) {
+    const int K = 1 << ceil_log2(4LL * p.Lq * p.P);
+    if (p.flags & kFlagDirectAll) {      // zero-fill, sample gradients and grad_value in one launch
+        auto ka = msda_grad_value_direct_kernel<T, TA, VEC, G, true>;
+        // cooperative launch (grid-wide barrier between the zero-fill and the row writes): the whole grid is resident
+        const int grid = num_sms() * msda_host::blocks_per_sm_cached(reinterpret_cast<const void*>(ka), kThreads, 0);
+        Params pa = p;
+        int k_arg = K < 4 ? 4 : K, id_bits = ceil_log2((long long)p.Lq * p.P);
+        void* args[] = {&pa, &k_arg, &id_bits};
+        prof_begin(st, "msda_bwd_direct_kernel");
+        MSDA_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(ka), dim3(grid), dim3(kThreads), args, 0, st));
+        prof_end(st);
+        MSDA_LAUNCHED("msda_bwd_direct_kernel");
+        return MSDA_OK;
+    }
     prof_begin(st, "memset(grad_value)");
     MSDA_CUDA(cudaMemsetAsync(p.grad_value, 0, (size_t)p.N * p.S * p.M * p.D * sizeof(T), st));
     prof_end(st);
     msda_host::count_launch();
     auto k = msda_grad_value_direct_kernel<T, TA, VEC, G>;
-    const int K = 1 << ceil_log2(4LL * p.Lq * p.P);
     prof_begin(st, "msda_grad_value_direct_kernel");
     k<<<persistent_grid(k, kThreads, (long long)p.N * p.M * p.L), kThreads, 0, st>>>(p, K < 4 ? 4 : K, ceil_log2((long long)p.Lq * p.P));
     prof_end(st);
@@ -559,7 +574,11 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
     const bool atomic_arm = (p.flags & MSDA_FLAG_ATOMIC_GRAD_VALUE) != 0;
     if (tile && direct_call(p.S, p.Lq, p.P, p.flags)) {
         if constexpr (!std::is_same<T, double>::value && !std::is_same<T, __half>::value) {
-            p.entries = nullptr;                 // part A keeps no index entries
+            p.entries = nullptr;                 // no index entries are kept
+            if (!(p.flags & (kFlagChain | MSDA_FLAG_DIRECT_SPLIT))) {
+                p.flags |= kFlagDirectAll;       // one launch: zero-fill + sample gradients + grad_value
+                return dispatch_grad_value_direct<TA>(p, pl, vdt, st);
+            }
             if ((rc = dispatch_bwd_sample_tile<TA>(p, pl, vdt, st))) return rc;
             return dispatch_grad_value_direct<TA>(p, pl, vdt, st);
         }
@@ -776,7 +795,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
                          unsigned flags, bool chain, const void* reference_points = nullptr) {
     msda_host::g_launches.store(0);
-    flags &= ~kFlagChain;
+    flags &= ~(kFlagChain | kFlagDirectAll);
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
     if (rc) return rc;

@@ -38,6 +38,8 @@
 //     Results are bit-identical from run to run.
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "msda_tiles.cuh"
 
 namespace msda {
@@ -943,7 +945,14 @@ __global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_
 constexpr int kDirectMax = 2048;    // contributions (4 per sample) of one (frame, head, level) held in shared memory
 constexpr int kDirectRows = 4096;   // grad_output elements of one (frame, head) staged in shared memory (fp32)
 
-template <typename T, typename TA, int VEC, int G>
+//
+// ALL (the default for these calls; cooperative launch): the whole backward in this one launch.
+//   * every CTA first zero-fills its share of grad_value (the reference's zeros_like, ms_deform_attn_cuda.cu:121) with
+//     128-bit stores, evenly over the grid; one grid-wide barrier later the touched rows are written over the zeros;
+//   * the CTA of (frame, head, level) also forms grad_sampling_loc / grad_attn_weight of the level's Lq*P samples
+//     (cuh:116-158: a lane group per sample reads the four corner rows, three partial sums are reduced over its lanes),
+// so that a decoder layer's backward is one kernel instead of memset + sample-gradient kernel + gather.
+template <typename T, typename TA, int VEC, int G, bool ALL = false>
 __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const Params p, const int K, const int id_bits) {
     constexpr int NG = kThreads / G;
     constexpr int D = VEC * G;
@@ -965,6 +974,14 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
     const bool staged = p.Lq * D <= kDirectRows;          // else the rows are read from global memory (L2)
     const int items = p.N * p.M * p.L;
     int nm_staged = -1;
+    if constexpr (ALL) {
+        uint4* gz = reinterpret_cast<uint4*>(gval);        // 16-byte aligned, a whole number of 16-byte words (tile path)
+        const size_t n16 = (size_t)p.N * p.S * p.M * p.D * sizeof(T) / 16;
+        for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += (size_t)gridDim.x * kThreads)
+            gz[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    bool zero_fill_done = !ALL;     // ALL: the grid-wide barrier comes right before this CTA's first row write, so that its
+                                    // first item's sample gradients and sort overlap the other CTAs' zero-fill
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int l = it % p.L;
         const int nm = it / p.L;
@@ -981,6 +998,56 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                 for (int c = 0; c < VEC; ++c) s_g[i * D + gl * VEC + c] = g[c];
             }
             nm_staged = nm;
+        }
+        if constexpr (ALL) {
+            // sample gradients of the level's Lq * P samples: one lane group per sample
+            const T* __restrict__ vb = static_cast<const T*>(p.value) + ((size_t)n * p.S * p.M + m) * p.D + gl * VEC;
+            TA* __restrict__ gloc = static_cast<TA*>(p.grad_loc);
+            TA* __restrict__ gattn = static_cast<TA*>(p.grad_attn);
+            const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+            if (staged) __syncthreads();                        // s_g of this (frame, head) is complete
+            for (int i = grp; i < nsamp; i += NG) {
+                const int q = i / p.P, pt = i - q * p.P;
+                const size_t si = (((size_t)n * p.Lq + q) * p.M + m) * p.LP + l * p.P + pt;
+                const XY<float> xy = load_xy(loc + 2 * si);
+                const float a = (float)ld_stream(attn + si);
+                const Sample<float> sm = locate(xy.x, xy.y, L_.H, L_.W);
+                float ga = 0.f, gx = 0.f, gy = 0.f;
+                if (sm.ok) {                                     // uniform over the lane group
+                    int pix[4];
+                    corner_pixels(sm, L_, pix);
+                    float v[4][VEC], g[VEC];
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) v[c4][c] = 0.f;
+                        if (pix[c4] >= 0) load_row<T, VEC>(vb + (size_t)pix[c4] * qstride, v[c4]);
+                    }
+                    if (staged) {
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) g[c] = s_g[q * D + gl * VEC + c];
+                    } else {
+                        load_row<T, VEC>(gbase + (size_t)q * qstride + gl * VEC, g);
+                    }
+                    const float hh = 1.f - sm.lh, hw = 1.f - sm.lw;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) {
+                        ga = fmaf(g[c], hh * (hw * v[0][c] + sm.lw * v[1][c]) + sm.lh * (hw * v[2][c] + sm.lw * v[3][c]), ga);
+                        gx = fmaf(g[c], hh * (v[1][c] - v[0][c]) + sm.lh * (v[3][c] - v[2][c]), gx);
+                        gy = fmaf(g[c], hw * (v[2][c] - v[0][c]) + sm.lw * (v[3][c] - v[1][c]), gy);
+                    }
+#pragma unroll
+                    for (int d = 1; d < G; d <<= 1) {
+                        ga += __shfl_xor_sync(gmask, ga, d, G);
+                        gx += __shfl_xor_sync(gmask, gx, d, G);
+                        gy += __shfl_xor_sync(gmask, gy, d, G);
+                    }
+                }
+                if (gl == 0) {
+                    gattn[si] = Elem<TA>::from_f(ga);
+                    store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
+                }
+            }
         }
         // 1. contributions
         for (int i = threadIdx.x; i < K / 4; i += kThreads) {
@@ -1038,6 +1105,12 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                 s_head[atomicAdd(&s_nhead, 1)] = (uint16_t)t;
         }
         __syncthreads();
+        if constexpr (ALL) {
+            if (!zero_fill_done) {                         // uniform over the CTA; every CTA passes exactly one grid barrier
+                cooperative_groups::this_grid().sync();
+                zero_fill_done = true;
+            }
+        }
         const int nhead = s_nhead;
         for (int r = grp; r < nhead; r += NG) {
             int t = s_head[r];
@@ -1065,6 +1138,9 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
             store_row<T, VEC>(gval + (((size_t)n * p.S + L_.start + pix) * p.M + m) * p.D + gl * VEC, acc);
         }
         __syncthreads();      // shared arrays are rewritten by the next item
+    }
+    if constexpr (ALL) {
+        if (!zero_fill_done) cooperative_groups::this_grid().sync();       // a CTA without items
     }
 }
 

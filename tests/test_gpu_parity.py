@@ -499,7 +499,9 @@ def test_grad_value_gathers_agree(kw, vdt, adt):
     """grad_value has two routes: the inverse-index pipeline (count / scan / fill / sort / walk) and, for calls
     with few queries per frame (4 * Lq * P <= 2048: decoder cross-attention), a direct gather that sorts one
     (frame, head, level)'s contributions in shared memory.  Forced either way, both must match the oracle and
-    leave grad_loc / grad_attn untouched; the direct one must be bit-reproducible and is the default here."""
+    leave grad_loc / grad_attn untouched (bit for bit with the three-launch sequence, which shares the sample-gradient
+    kernel with the index pipeline; to rounding with the one-launch kernel, which reduces over lanes in another order);
+    the direct one must be bit-reproducible and is the default here."""
     if vdt == torch.float32 and adt != torch.float32:
         pytest.skip("fp32 values take fp32 locations")
     x = make_inputs(seed=17, **kw)
@@ -507,13 +509,16 @@ def test_grad_value_gathers_agree(kw, vdt, adt):
     dense = run_op(*a, vdt, adt, flags=_lib.FLAG_WALK_DENSE)
     direct = run_op(*a, vdt, adt)
     direct2 = run_op(*a, vdt, adt)
+    split = run_op(*a, vdt, adt, flags=_lib.FLAG_DIRECT_SPLIT)
     v, lo, at, go = dense[4]
     r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
     tol = TOL[vdt]
     assert rel_err(dense[1], r_gv) <= tol and rel_err(direct[1], r_gv) <= tol
-    assert torch.equal(direct[1], direct2[1])
+    assert torch.equal(direct[1], direct2[1]) and torch.equal(direct[1], split[1])
     for i in (0, 2, 3):
-        assert torch.equal(dense[i], direct[i])
+        assert torch.equal(dense[i], split[i])
+        assert torch.equal(direct[i], direct2[i])
+        assert rel_err(direct[i], dense[i].double().cpu().numpy()) <= tol
     N, S, M, D = x.value.shape
     Lq, L, P = x.sampling_locations.shape[1], x.sampling_locations.shape[3], x.sampling_locations.shape[4]
     assert _lib.load().msda_index_bytes(N, S, M, D, L, Lq, P) == 0       # no index handoff for these shapes
@@ -676,3 +681,64 @@ def test_large_channel_counts_of_the_reference_test(D):
     x = make_inputs(N=1, dist="uniform", shapes=[(6, 4), (3, 2)], M=2, D=D, Lq=2, P=2, seed=91, value_scale=0.01)
     _check_against_oracle(x, torch.float64, torch.float64, tol=1e-11)
     _check_against_oracle(x, torch.float32, torch.float32, tol=1e-5)
+
+
+# ---------------------------------------------------------------------------- decoder-shaped backward in one launch
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("kw", [dict(N=16, dist="decoder", Lq=20), dict(N=36, dist="decoder", Lq=5),
+                                dict(N=2, dist="decoder", Lq=100, P=4), dict(N=3, dist="uniform", Lq=7, P=8, D=64, M=2, shapes=[(9, 11), (5, 6)])])
+def test_one_launch_decoder_backward(kw, vdt, adt):
+    """Calls with few queries per frame run their whole backward in ONE kernel (zero-fill of grad_value, sample
+    gradients, direct gather); MSDA_FLAG_DIRECT_SPLIT keeps the three-launch sequence.  Same grad_value bits (the
+    gather is the same), sample gradients equal to rounding, both against the fp64 oracle, and the launch counts."""
+    x = make_inputs(seed=95, **kw)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    one = run_op(*a, vdt, adt)
+    n_one = msda_ext.last_launch_count()
+    split = run_op(*a, vdt, adt, flags=_lib.FLAG_DIRECT_SPLIT)
+    n_split = msda_ext.last_launch_count()
+    assert n_one == 1 and n_split == 3
+    assert torch.equal(one[1], split[1])
+    v, lo, at, go = one[4]
+    r_out, r_gv, r_gl, r_ga = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)
+    keep = off_lattice(lo.double().cpu().numpy(), x.spatial_shapes.numpy(), 1e-3)
+    tol = TOL[vdt] if adt == vdt or vdt == torch.float32 else TOL[torch.bfloat16]
+    for got in (one, split):
+        assert rel_err(got[1], r_gv) <= tol
+        assert rel_err(got[3], r_ga) <= tol
+        assert rel_err(got[2], r_gl, keep) <= 2 * tol
+
+
+def test_one_launch_decoder_backward_zero_fills_gaps_and_untouched_rows():
+    x = make_inputs(N=2, dist="decoder", shapes=[(5, 6), (3, 4)], M=4, D=32, Lq=6, seed=96)
+    S2 = 30 + 7 + 12 + 5                                  # 7 unused rows between the levels, 5 at the end
+    value = torch.randn(2, S2, 4, 32, generator=torch.Generator().manual_seed(1))
+    lsi = torch.tensor([0, 37], dtype=torch.long)
+    dev = [t.to(DEV) for t in (value, x.spatial_shapes, lsi, x.sampling_locations, x.attention_weights, x.grad_output)]
+    poison = torch.full_like(dev[0], float("nan"))
+    gv, gl, ga = msda_ext.ms_deform_attn_backward(*dev[:5], dev[5], 64, grads=(poison, torch.empty_like(dev[3]), torch.empty_like(dev[4])))
+    assert msda_ext.last_launch_count() == 1
+    assert torch.isfinite(gv).all()                       # every row was written
+    assert float(gv[:, 30:37].abs().max()) == 0.0 and float(gv[:, 49:].abs().max()) == 0.0
+    r = oracle_f64(dev[0].cpu(), x.spatial_shapes, lsi, dev[3].cpu(), dev[4].cpu(), dev[5].cpu())
+    assert rel_err(gv, r[1]) <= 1e-5
+
+
+def test_one_launch_decoder_backward_in_a_cuda_graph():
+    """The one-launch backward is a cooperative launch (grid-wide barrier between zero-fill and row writes): it must
+    survive stream capture and replay like the other kernels."""
+    x = make_inputs(N=16, dist="decoder", Lq=20, seed=97).to(DEV)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
+    grads = (torch.empty_like(x.value), torch.empty_like(x.sampling_locations), torch.empty_like(x.attention_weights))
+    ws = torch.empty(max(16, msda_ext.backward_workspace_bytes(x.value, x.sampling_locations)), dtype=torch.uint8, device=DEV)
+    eager = [t.clone() for t in msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64, grads=grads, workspace=ws)]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64, grads=grads, workspace=ws)
+    for t in grads:
+        t.fill_(float("nan"))
+    g.replay()
+    torch.cuda.synchronize()
+    for u, w in zip(grads, eager):
+        assert torch.equal(u, w)
