@@ -381,9 +381,9 @@ void walk_dense_tile(const Params& p, int& thd, int& twd) {
     if (env) { int a = 0, b = 0; if (sscanf(env, "%dx%d", &a, &b) == 2 && a > 0 && b > 0) { thd = a; twd = b; } }
 }
 
-template <typename T, int VEC, int G>
+template <typename T, int VEC, int G, int TWT = kGTileW, int BRT = 0>
 int launch_grad_value_walk(const Params& p, cudaStream_t st) {
-    auto k = msda_grad_value_walk_kernel<T, VEC, G>;
+    auto k = msda_grad_value_walk_kernel<T, VEC, G, TWT, BRT>;
     int thd, twd;
     walk_dense_tile(p, thd, twd);
     // tiles per (frame, head) are only known on the device; S / 8 bounds them from above
@@ -530,6 +530,8 @@ int dispatch_grad_value_walk(const Params& p, const Plan& pl, int vdt, cudaStrea
         }
     }
     using B = __nv_bfloat16;
+    static const bool g4 = getenv("MSDA_WALK_G4") != nullptr;      // experiment: 64-byte bf16 rows on 4 lanes x 128 bit
+    if (g4 && pl.wvec == 4 && pl.wg == 8) return launch_grad_value_walk<B, 8, 4, 4, 32>(p, st);
     if (pl.wvec == 4) return pl.wg == 8 ? launch_grad_value_walk<B, 4, 8>(p, st) : launch_grad_value_walk<B, 4, 16>(p, st);
     return launch_grad_value_walk<B, 8, 16>(p, st);
 }

@@ -702,6 +702,9 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
 #ifndef MSDA_WALK_MIN_BLOCKS
 #define MSDA_WALK_MIN_BLOCKS 6
 #endif
+#ifndef MSDA_WALK_G4_MIN_BLOCKS
+#define MSDA_WALK_G4_MIN_BLOCKS 5
+#endif
 
 // CTAs per SM, measured on B200 at the A2D shape (D = 32): bf16 rows 5 / 6 / 7 / 8 -> 283 / 283 / 263 / 278 us,
 // fp32 rows 5 / 6 / 7 -> 321 / 333 / 360 us (the kernel is latency-bound; registers vs. rows in flight)
@@ -710,13 +713,15 @@ constexpr int walk_min_blocks() {
     return (G == 8 && VEC == 4) ? (sizeof(T) == 2 ? 7 : 5) : MSDA_WALK_MIN_BLOCKS;
 }
 
-template <typename T, int VEC, int G>
-__global__ void __launch_bounds__(kGThreads, walk_min_blocks<T, VEC, G>()) msda_grad_value_walk_kernel(const Params p, const int thd, const int twd) {
+// TWT / BRT: tile width in pixels and bin rows per tile (0: one bin row per 128-bit fp32 lane group, 512 / D).  The
+// 4-lane variant for 64-byte bf16 rows (VEC = 8, G = 4) has 32 lane groups per CTA: 32 bin rows x 4 pixels.
+template <typename T, int VEC, int G, int TWT = kGTileW, int BRT = 0>
+__global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : walk_min_blocks<T, VEC, G>())) msda_grad_value_walk_kernel(const Params p, const int thd, const int twd) {
     constexpr int D = VEC * G;
     constexpr int NGRP = kGThreads / G;          // groups per CTA
     constexpr int GW = 32 / G;                   // groups per warp
-    constexpr int BR = (512 / D) < 2 ? 2 : (512 / D);   // bin rows per tile
-    constexpr int TH = BR - 1, TW = kGTileW;
+    constexpr int BR = BRT ? BRT : ((512 / D) < 2 ? 2 : (512 / D));   // bin rows per tile
+    constexpr int TH = BR - 1, TW = TWT;
 #ifndef MSDA_WALK_STEP
 #define MSDA_WALK_STEP 4
 #endif
