@@ -11,7 +11,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 OUT, PROF = ROOT / "gpurun_out", ROOT / "profiles"
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 COPY = {
     "launches_bench.csv": f"{TAG}_launches_bench.csv", "launches_fp32.csv": f"{TAG}_launches_fp32.csv",
@@ -20,6 +20,9 @@ COPY = {
     "inference_bench.jsonl": f"{TAG}_inference_bench.jsonl", "sweep.jsonl": f"{TAG}_sweep_config5.jsonl",
     "host_pipeline_timeline.txt": f"{TAG}_host_pipeline_timeline.txt", "probe_n2.json": f"{TAG}_probe_encoder_n2.json",
     "probe_n16.json": f"{TAG}_probe_encoder_uniform.json", "bench_n2.json": f"{TAG}_bench_n2.json",
+    "soc_step_n1.json": f"{TAG}_soc_n1.json", "level_breakdown.jsonl": f"{TAG}_level_breakdown.jsonl",
+    "reference_stack_parity.txt": f"{TAG}_reference_stack_parity.txt", "reference_test_py.txt": f"{TAG}_reference_test_py.txt",
+    "pytest_gpu.log": f"{TAG}_pytest_gpu.log",
 }
 for src, dst in COPY.items():
     if (OUT / src).exists():
@@ -74,7 +77,10 @@ want = {
     "bwd_sample_tile_bf16": "msda_bwd_sample_tile_kernelI13__nv_bfloat16fLi8ELi4ELi4ELb1ELb0ELi512E",
     "grad_value_walk_bf16": "msda_grad_value_walk_kernelI13__nv_bfloat16Li4ELi8E",
     "bin_rank_sort_f32": "msda_bin_rank_sort_kernelIfE",
-    "grad_value_direct_f32": "msda_grad_value_direct_kernelIffLi4ELi8E",
+    "grad_value_direct_f32": "msda_grad_value_direct_kernelIffLi4ELi8ELb1E",
+    "bwd_bin_bf16": "msda_bwd_bin_kernelI13__nv_bfloat16Li8ELi4E",
+    "add_layernorm_fwd_bf16": "msda_add_layernorm_fwd_kernelI13__nv_bfloat16E",
+    "add_layernorm_bwd_bf16": "msda_add_layernorm_bwd_kernelI13__nv_bfloat16E",
 }
 blocks = names.split("\t\tFunction : ")
 for tag, key in want.items():

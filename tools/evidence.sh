@@ -15,7 +15,7 @@ for dt in fp32 bf16mix; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:msda --csv --log-file gpurun_out/launches_$dt.csv python tools/one_step.py --dtype $dt --steps 2 > /dev/null 2>&1
 done
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"msda_(fwd_tile|bwd_sample_tile|bin_rank_sort|grad_value_walk)" -s 8 -c 4 -o gpurun_out/full_bf16mix python tools/one_step.py --dtype bf16mix --steps 3 > gpurun_out/ncu_full.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"msda_bwd_direct" -c 1 -o gpurun_out/full_direct python tools/kernel_times.py --lq 20 --dtype fp32 --steps 1 > /dev/null 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"msda_grad_value_direct" -c 1 -o gpurun_out/full_direct python tools/kernel_times.py --lq 20 --dtype fp32 --steps 1 > /dev/null 2>&1
 # gpurun brings back at most 64 MiB: keep the raw-metric pages, not the reports
 for r in full_bf16mix full_direct; do
   ncu -i gpurun_out/$r.ncu-rep --page raw --csv > gpurun_out/$r.raw.csv 2>/dev/null
