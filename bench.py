@@ -25,6 +25,8 @@ Printed JSON line (rank 0): metric/value/unit..., plus
                   kernel; `l1_wavefront` is the gather ceiling of DESIGN.md section 5, clearly not the HBM one
   ref_cuda     -- the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref, when shipped) timed on
                   the same fp32 tensors beside this repo's kernels: the GPU bar to beat
+  unordered    -- the same step with MSDA_FLAG_UNORDERED (opt-in: no rank sort, grad_value in arrival order like the
+                  reference's atomics): what bit-reproducibility costs; `value` is always the reproducible default
   cpu_baseline -- the reference's CPU formulation (ms_deform_attn_core_pytorch: the staged reference file
                   when baseline/_ref/soc exists, else its restatement in oracle/) timed on this box's host cores
   e2e          -- the same step through the host entry point (host_frames.HostFramePipeline) with inputs in
@@ -218,8 +220,8 @@ class DeviceStep:
     the backward's workspace, the forward's index) -- what MSDeformAttnFunction does minus the allocator calls --
     optionally captured in a CUDA graph."""
 
-    def __init__(self, x, msda_ext, graph: bool):
-        self.x, self.ext = x, msda_ext
+    def __init__(self, x, msda_ext, graph: bool, flags=None):
+        self.x, self.ext, self.flags = x, msda_ext, flags
         self.args = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
         N, S, M, D = x.value.shape
         Lq = x.sampling_locations.shape[1]
@@ -248,7 +250,8 @@ class DeviceStep:
     def eager(self):
         _, index = self.ext.ms_deform_attn_forward(*self.args, 64, want_index=True, out=self.out, index_buf=self.index)
         lf = self.ext.last_launch_count()
-        self.ext.ms_deform_attn_backward(*self.args, self.x.grad_output, 64, index=index, grads=self.grads, workspace=self.ws)
+        self.ext.ms_deform_attn_backward(*self.args, self.x.grad_output, 64, index=index, grads=self.grads, workspace=self.ws,
+                                         flags=self.flags)
         self.launches = lf + self.ext.last_launch_count()
 
     def __call__(self):
@@ -337,6 +340,27 @@ def run_ours(args):
     eager_ms = None
     if step.graph is not None:    # the same step issued call by call, for the record
         eager_ms = time_steps(step.eager, min(args.steps, 50), 3)
+
+    # ---- what bit-reproducibility costs: the same step with MSDA_FLAG_UNORDERED (no rank sort; grad_value summed in
+    # arrival order, the reference's own behaviour).  For the record only: `value` above is the reproducible default.
+    unordered = None
+    if rank == 0 and world == 1:
+        su = DeviceStep(x, msda_ext, graph=not args.no_graph, flags=_lib.FLAG_UNORDERED)
+        n_u = min(args.steps, 50)
+        for _ in range(3):
+            su()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_u):
+            su()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_u = e0.elapsed_time(e1) / n_u
+        unordered = {"flag": "MSDA_FLAG_UNORDERED", "ms_per_step": ms_u, "value": total_queries / (ms_u * 1e-3), "unit": UNIT,
+                     "steps": n_u, "launches_per_step": su.launches,
+                     "note": "opt-in; grad_value not bit-reproducible from run to run (like the reference's atomicAdd)"}
+        del su
 
     # ---- strong scaling beside a weak run: 16 frames in total over the same ranks ----
     strong = None
@@ -557,7 +581,7 @@ def run_ours(args):
             "config": cfg,
             "eager_ms_per_step": eager_ms,
             "roofline": roofline, "ref_cuda": ref_cuda, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "strong_scaling": strong,
+            "strong_scaling": strong, "unordered": unordered,
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(),
         })

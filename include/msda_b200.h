@@ -85,6 +85,11 @@ enum msda_status {
                                       measured slower on B200, kept for comparison */
 #define MSDA_FLAG_DIRECT_SPLIT 64u  /* A/B: decoder-shaped backward as memset + sample-gradient kernel + direct gather
                                       (three launches) instead of the one kernel that does all three */
+#define MSDA_FLAG_UNORDERED 128u    /* opt-in: skip the rank sort of the inverse index.  grad_value is then summed in the
+                                       order the index entries happened to be written (integer-atomic slots), i.e. it may
+                                       differ in the last bits from run to run -- what the reference's atomicAdd scatter does
+                                       all the time (ms_deform_im2col_cuda.cuh:116-153).  grad_sampling_loc and
+                                       grad_attn_weight are unaffected.  Off by default: the default is bit-reproducible */
 #define MSDA_FLAG_WALK_DENSE 16u   /* force the inverse-index pipeline for grad_value even when the call is small enough
                                       for the direct shared-memory gather (decoder-shaped calls, Lq * P <= 512) */
 

@@ -16,6 +16,7 @@ FLAG_PYRAMID_TILES, FLAG_GENERIC, FLAG_ATOMIC_GRAD_VALUE, FLAG_BF16_VEC4 = 1, 2,
 FLAG_WALK_DENSE = 16
 FLAG_BIN_KERNEL = 32
 FLAG_DIRECT_SPLIT = 64
+FLAG_UNORDERED = 128
 
 EXPORTS = (
     "msda_version", "msda_last_error", "msda_forward", "msda_forward_ex",

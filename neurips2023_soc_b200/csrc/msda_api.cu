@@ -42,11 +42,16 @@ struct ProfRec {
 std::mutex g_prof_mu;
 std::atomic<bool> g_prof{false};
 std::vector<ProfRec> g_recs;
+constexpr size_t kProfMax = 1u << 16;   // records (two CUDA events each) kept per msda_profile_enable(1)
 }  // namespace
 
 void prof_begin(cudaStream_t st, const char* name) {
     if (!g_prof.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_recs.size() >= kProfMax) {     // a forgotten profile stops recording instead of growing without bound
+        g_prof.store(false);
+        return;
+    }
     ProfRec r{name, nullptr, nullptr};
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
@@ -537,9 +542,11 @@ int dispatch_grad_value_walk(const Params& p, const Plan& pl, int vdt, cudaStrea
 }
 
 // Sub-bins per (frame, head) are only known on the device; bound them: sum_l nb_l * nch_l with
-// nb_l = (H_l+1)(W_l+1) and nch_l < 2 * (Lq*P / (6 nb_l) + 1)  =>  < L*Lq*P/3 + 2 * sum nb_l, and
+// nb_l = (H_l+1)(W_l+1) and nch_l < 2 * (Lq*P / (T nb_l) + 1), T = kSubBinTarget  =>  < 2*L*Lq*P/T + 2 * sum nb_l, and
 // sum nb_l <= 2S + 2L.
-int sub_bin_bound(int S, int L, int Lq, int P) { return (int)((long long)L * Lq * P / 3 + 4LL * S + 4LL * L + 1); }
+int sub_bin_bound(int S, int L, int Lq, int P) {
+    return (int)(2LL * L * Lq * P / kSubBinTarget + 4LL * S + 4LL * L + 1);
+}
 
 size_t index_bytes(int N, int S, int M, int L, int Lq, int P) {
     return (size_t)N * M * (sub_bin_bound(S, L, Lq, P) + 1) * sizeof(uint32_t);
@@ -613,7 +620,7 @@ int backward_typed(Params& p, const Plan& pl, int vdt, void* index, size_t table
         // A/B: sort + sum in one kernel over shared-memory pixel tiles (msda_bwd_bin.cuh)
         return msda_host::launch_grad_value_tile(p, vdt, vdt == MSDA_F32 ? 4 : 8, vdt == MSDA_F32 ? p.D / 4 : p.D / 8, st);
     }
-    if ((rc = launch_sort<CT>(p, st))) return rc;
+    if (!(p.flags & MSDA_FLAG_UNORDERED) && (rc = launch_sort<CT>(p, st))) return rc;
     if (tile) return dispatch_grad_value_walk(p, pl, vdt, st);
     return launch_grad_value_generic<T, CT>(p, st);
 }
@@ -674,6 +681,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
                         int M, int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
                         void* cuda_stream, unsigned flags) {
     msda_host::g_launches.store(0);
+    const msda_host::DeviceGuard guard(value);   // the device that owns `value` is current for this call
     const bool fused = reference_points != nullptr;
     if (fused) {   // the raw offsets / logits may be bf16 next to fp32 values only through the value dtype rule below
         if ((loc_out == nullptr) != (attn_out == nullptr))
@@ -685,6 +693,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
                           Lq, P, value_dtype, aux_dtype, im2col_step);
     if (rc) return rc;
     if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "null output pointer");
+    if (!guard.ok()) return fail(MSDA_ERR_INVALID_ARGUMENT, "value must be device memory (a CUDA tensor)");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 
     Params p;
@@ -797,6 +806,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
                          unsigned flags, bool chain, const void* reference_points = nullptr) {
     msda_host::g_launches.store(0);
+    const msda_host::DeviceGuard guard(value);   // the device that owns `value` is current for this call
     flags &= ~(kFlagChain | kFlagDirectAll);
     int rc = check_common(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L,
                           Lq, P, value_dtype, aux_dtype, im2col_step);
@@ -821,6 +831,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
     if (index && msda_index_bytes(N, S, M, D, L, Lq, P) == 0) index = nullptr;   // no handoff for this shape
     if (index && index_size < table_bytes)
         return fail(MSDA_ERR_WORKSPACE, "index buffer of %zu bytes required, got %zu", table_bytes, index_size);
+    if (!guard.ok()) return fail(MSDA_ERR_INVALID_ARGUMENT, "value must be device memory (a CUDA tensor)");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
 
     Params p;

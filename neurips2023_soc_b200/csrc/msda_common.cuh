@@ -22,7 +22,10 @@ constexpr int kMaxLevels = 16;   // levels held in shared memory per CTA
 constexpr int kThreads = 256;    // CTA size of the tile kernels
 constexpr int kSC = 16;          // samples staged per chunk (L*P = 16 in every SOC config)
 constexpr int kDescStride = kSC + 1;  // 16 B slots per query in the descriptor arrays (+1: bank skew)
-constexpr int kSubBinTarget = 6;      // aimed-at entries per sub-bin (see Level::nch_log2)
+#ifndef MSDA_SUB_BIN_TARGET
+#define MSDA_SUB_BIN_TARGET 6
+#endif
+constexpr int kSubBinTarget = MSDA_SUB_BIN_TARGET;   // aimed-at entries per sub-bin (see Level::nch_log2)
 constexpr int kMaxSubLog2 = 8;
 constexpr int kTileW = 16;       // pyramid query tile: kTileH x kTileW pixels of one level
 constexpr int kTileH = 8;

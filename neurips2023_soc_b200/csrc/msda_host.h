@@ -23,6 +23,28 @@ void count_launch();
 
 int num_sms();
 
+// SURVEY.md section 8b asks for an explicit device: the ABI takes pointers, and a pointer names its device.  Every
+// entry point runs under this guard: the device that owns `ptr` becomes current for the call (the reference has no
+// guard and relies on torch.cuda.set_device, /root/reference/trainer.py:447), the previous one is restored on return.
+// ok() is false when `ptr` is not device (or managed) memory at all.
+class DeviceGuard {
+public:
+    explicit DeviceGuard(const void* ptr) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+        ok_ = true;
+        if (cudaGetDevice(&prev_) == cudaSuccess && prev_ != a.device) switched_ = cudaSetDevice(a.device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched_) cudaSetDevice(prev_); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+    bool ok() const { return ok_; }
+private:
+    int prev_ = -1;
+    bool ok_ = false, switched_ = false;
+};
+
 // cudaOccupancyMaxActiveBlocksPerMultiprocessor, cached per (kernel, device, dynamic smem).
 int blocks_per_sm_cached(const void* kernel, int threads, size_t dyn_smem);
 

@@ -199,6 +199,8 @@ int msda_add_layernorm_forward(const void* branch, const void* residual, const f
     if (dtype != MSDA_F32 && dtype != MSDA_BF16) return msda_host::fail(MSDA_ERR_UNSUPPORTED, "add + LayerNorm takes fp32 or bf16 rows");
     if (!(aligned16(branch) && aligned16(residual) && aligned16(gamma) && aligned16(beta) && aligned16(out) && aligned16(presum)))
         return msda_host::fail(MSDA_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
+    const msda_host::DeviceGuard guard(branch);
+    if (!guard.ok()) return msda_host::fail(MSDA_ERR_INVALID_ARGUMENT, "branch must be device memory (a CUDA tensor)");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     msda_host::prof_begin(st, "msda_add_layernorm_fwd_kernel");
     if (dtype == MSDA_F32)
@@ -227,6 +229,8 @@ int msda_add_layernorm_backward(const void* grad_out, const void* presum, const 
         return msda_host::fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
     if (!(aligned16(grad_out) && aligned16(presum) && aligned16(gamma) && aligned16(grad_in) && aligned16(workspace)))
         return msda_host::fail(MSDA_ERR_INVALID_ARGUMENT, "tensors must be 16-byte aligned");
+    const msda_host::DeviceGuard guard(grad_out);
+    if (!guard.ok()) return msda_host::fail(MSDA_ERR_INVALID_ARGUMENT, "grad_out must be device memory (a CUDA tensor)");
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     float* part = static_cast<float*>(workspace);
     const int grid = ln_grid(rows);

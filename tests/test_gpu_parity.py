@@ -49,7 +49,8 @@ def run_op(value, shapes, lsi, loc, attn, grad_out, vdt, adt, flags=0):
         # the index handed over by the forward must reproduce the self-counted backward bit for bit
         out2, index = msda_ext.ms_deform_attn_forward(v, sh, ls, lo, at, 64, flags=flags, want_index=True)
         gv2, gl2, ga2 = msda_ext.ms_deform_attn_backward(v, sh, ls, lo, at, go, 64, flags=flags, index=index)
-        assert torch.equal(out, out2) and torch.equal(gv, gv2) and torch.equal(gl, gl2) and torch.equal(ga, ga2)
+        assert torch.equal(out, out2) and torch.equal(gl, gl2) and torch.equal(ga, ga2)
+        assert (flags & _lib.FLAG_UNORDERED) or torch.equal(gv, gv2)     # unordered: same terms, arrival order
     torch.cuda.synchronize()
     return out, gv, gl, ga, (v, lo, at, go)
 
@@ -612,6 +613,59 @@ def test_grad_value_bin_kernel_vs_sort_and_walk(kw, vdt, adt):
     assert rel_err(new[1], r_gv) <= tol
     assert rel_err(old[1], r_gv) <= tol
     assert torch.equal(new[0], old[0]) and torch.equal(new[2], old[2]) and torch.equal(new[3], old[3])
+
+
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_unordered_flag_skips_the_sort_only(vdt, adt):
+    """MSDA_FLAG_UNORDERED (opt-in) leaves the index entries in arrival order: grad_value is the same sum in another
+    order (within the dtype's bound of the fp64 oracle, like the reference's atomics), the sample gradients and the
+    output are the same bits, and no sort kernel is launched."""
+    x = make_inputs(N=2, dist="encoder", seed=85)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights, x.grad_output)
+    _lib.profile_enable(True)
+    new = run_op(*a, vdt, adt, flags=_lib.FLAG_UNORDERED)
+    torch.cuda.synchronize()
+    names = [n for n, _ in _lib.profile_read()]
+    _lib.profile_enable(False)
+    assert "msda_grad_value_walk_kernel" in names and not any("sort" in n for n in names), names
+    old = run_op(*a, vdt, adt)
+    v, lo, at, go = new[4]
+    r_gv = oracle_f64(v, x.spatial_shapes, x.level_start_index, lo, at, go)[1]
+    assert rel_err(new[1], r_gv) <= TOL[vdt]
+    assert torch.equal(new[0], old[0]) and torch.equal(new[2], old[2]) and torch.equal(new[3], old[3])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_c_abi_runs_on_the_device_that_owns_the_pointers(monkeypatch):
+    """the ABI names its device through the pointers.  With device 0 current and no device context around
+    the call (torch.cuda.device patched out of the shim), tensors on cuda:1 are processed on cuda:1 and device 0 is
+    current again afterwards."""
+    x = make_inputs(N=1, dist="encoder", seed=86).to("cuda:1", torch.float32, torch.float32)
+    a = (x.value, x.spatial_shapes, x.level_start_index, x.sampling_locations, x.attention_weights)
+    ref_out = msda_ext.ms_deform_attn_forward(*a, 64)
+    ref_g = msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64)
+    torch.cuda.synchronize(1)
+
+    class NoDeviceContext:
+        def __init__(self, *args):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    torch.cuda.set_device(0)
+    monkeypatch.setattr(torch.cuda, "device", NoDeviceContext)
+    out = msda_ext.ms_deform_attn_forward(*a, 64)          # stream: device 0's current stream = the default stream
+    g = msda_ext.ms_deform_attn_backward(*a, x.grad_output, 64)
+    monkeypatch.undo()
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(1)
+    assert torch.equal(out, ref_out)
+    for u, w in zip(g, ref_g):
+        assert torch.equal(u, w)
 
 
 @pytest.mark.parametrize("flags", [0, _lib.FLAG_BIN_KERNEL])
