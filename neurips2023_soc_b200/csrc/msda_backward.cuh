@@ -702,15 +702,21 @@ __device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restric
 #ifndef MSDA_WALK_MIN_BLOCKS
 #define MSDA_WALK_MIN_BLOCKS 6
 #endif
+#ifndef MSDA_WALK_MB_BF16
+#define MSDA_WALK_MB_BF16 7
+#endif
+#ifndef MSDA_WALK_MB_F32
+#define MSDA_WALK_MB_F32 6
+#endif
 #ifndef MSDA_WALK_G4_MIN_BLOCKS
 #define MSDA_WALK_G4_MIN_BLOCKS 5
 #endif
 
-// CTAs per SM, measured on B200 at the A2D shape (D = 32): bf16 rows 5 / 6 / 7 / 8 -> 283 / 283 / 263 / 278 us,
-// fp32 rows 5 / 6 / 7 -> 321 / 333 / 360 us (the kernel is latency-bound; registers vs. rows in flight)
+// CTAs per SM, measured on B200 at the A2D shape (D = 32) with the lockstep loops: bf16 rows 6 / 7 / 8 -> 267 / 247 / 259 us,
+// fp32 rows 4 / 5 / 6 -> 388 / 314 / 288 us (registers vs. rows in flight)
 template <typename T, int VEC, int G>
 constexpr int walk_min_blocks() {
-    return (G == 8 && VEC == 4) ? (sizeof(T) == 2 ? 7 : 5) : MSDA_WALK_MIN_BLOCKS;
+    return (G == 8 && VEC == 4) ? (sizeof(T) == 2 ? MSDA_WALK_MB_BF16 : MSDA_WALK_MB_F32) : MSDA_WALK_MIN_BLOCKS;
 }
 
 // TWT / BRT: tile width in pixels and bin rows per tile (0: one bin row per 128-bit fp32 lane group, 512 / D).  The
@@ -770,7 +776,6 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = tid / G, gl = tid % G, gw = lane / G;    // gw: group index inside the warp
-    const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - gl));
     const int total_tiles = tstart[p.L];
     const size_t per_nm = (size_t)p.Lq * p.LP;
     const size_t qstride = (size_t)p.M * p.D;
@@ -800,19 +805,26 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
         const Entry<float>* ent = entries + nm * per_nm;
         const T* gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
 
+        // The lane groups of a warp run every loop below in lockstep, whatever their own rows and bins hold: trip
+        // counts are warp-wide (votes), a group with nothing left works on empty batches (zero weights, no loads).
+        // A warp that lets its groups leave a loop at different times pays for it at every shuffle afterwards
+        // (ptxas routes shuffles of a diverged warp through a WARPSYNC.COLLECTIVE slow path, ~9 instructions each).
+        constexpr uint32_t kFull = 0xffffffffu;
         const int row_first = dense ? warp : grp;
         const int row_step = dense ? NWARP : NGRP;
-        for (int row = row_first; row <= th_l; row += row_step) {
+        for (int rbase = 0; rbase <= th_l; rbase += row_step) {
+            const int row = rbase + row_first;
             const int by = y0 + row;
-            if (by > L_.H) break;
-            const bool emit_t = row >= 1;                              // pixel row by-1 is in the tile
-            const bool emit_b = row <= th_l - 1 && by <= L_.H - 1;     // pixel row by is in the tile
+            const bool live = row <= th_l && by <= L_.H;               // this group has a bin row to walk
+            if (GW > 1 ? !__any_sync(kFull, live) : !live) continue;   // no group of the warp has one
+            const bool emit_t = live && row >= 1;                      // pixel row by-1 is in the tile
+            const bool emit_b = live && row <= th_l - 1 && by <= L_.H - 1;     // pixel row by is in the tile
             float* const tdst = sT + (row - 1) * TW * D + gl * VEC;
             float* const bdst = sB + row * TW * D + gl * VEC;
 
             // Entry offsets at the bin boundaries of the row segment, read one bin ahead.
-            const uint32_t* orow = off + L_.bin_start + ((by * (L_.W + 1) + x0) << L_.nch_log2);
-            auto bound = [&](const int j) { return orow[min(j, nb) << L_.nch_log2]; };
+            const uint32_t* orow = off + L_.bin_start + (((live ? by : y0) * (L_.W + 1) + x0) << L_.nch_log2);
+            auto bound = [&](const int j) { return live ? orow[min(j, nb) << L_.nch_log2] : 0u; };
             // the share of bin [lo, hi) this group works on: all of it, or 1/GW of it in dense levels
             auto share = [&](const uint32_t lo, const uint32_t hi, uint32_t& r0, uint32_t& r1) {
                 if (!dense) { r0 = lo; r1 = hi; return; }
@@ -837,31 +849,39 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
             for (int b = 0; b < nb; ++b) {
                 const uint32_t b_nn = bound(b + 3);                 // boundary needed two bins from now
                 uint32_t e0 = r0;
+                bool active = true;                                 // batches of this bin left for this group
                 while (true) {
-                    const Entry<float> mine = nxt;
-                    const bool more = e0 + G < r1;
-                    nxt = more ? load_entry(ent, e0 + G + gl, r1) : load_entry(ent, n0 + gl, n1);
-                    const int nbat = e0 < r1 ? (int)min((uint32_t)G, r1 - e0) : 0;
+                    Entry<float> mine;
+                    mine.id = 0; mine.lh = mine.lw = mine.a = 0.f;
+                    int nbat = 0;
+                    if (active) {
+                        mine = nxt;
+                        const bool more = e0 + G < r1;
+                        nxt = more ? load_entry(ent, e0 + G + gl, r1) : load_entry(ent, n0 + gl, n1);
+                        nbat = e0 < r1 ? (int)min((uint32_t)G, r1 - e0) : 0;
+                        active = more;
+                        e0 += G;
+                    }
                     const float ah = mine.a * (1.f - mine.lh), al = mine.a * mine.lh, hw = 1.f - mine.lw;
                     const float myw[4] = {ah * hw, ah * mine.lw, al * hw, al * mine.lw};
                     const uint32_t myq = mine.id >> p.id_shift;
 #pragma unroll
                     for (int c0 = 0; c0 < G; c0 += STEP) {
-                        if (c0 >= nbat) break;
+                        if (GW > 1 ? !__any_sync(kFull, c0 < nbat) : c0 >= nbat) break;
                         using R = typename Raw<sizeof(T) * VEC>::type;
                         R raw[STEP];
 #pragma unroll
                         for (int e = 0; e < STEP; ++e) {
-                            const uint32_t q = __shfl_sync(gmask, myq, c0 + e, G);
+                            const uint32_t q = __shfl_sync(kFull, myq, c0 + e, G);
                             // entries past nbat carry zero weights and zero rows
                             raw[e] = load_raw_if<T, VEC>(c0 + e < nbat, gbase + (size_t)q * qstride);
                         }
 #pragma unroll
                         for (int e = 0; e < STEP; ++e) {
-                            const float w0 = __shfl_sync(gmask, myw[0], c0 + e, G);
-                            const float w1 = __shfl_sync(gmask, myw[1], c0 + e, G);
-                            const float w2 = __shfl_sync(gmask, myw[2], c0 + e, G);
-                            const float w3 = __shfl_sync(gmask, myw[3], c0 + e, G);
+                            const float w0 = __shfl_sync(kFull, myw[0], c0 + e, G);
+                            const float w1 = __shfl_sync(kFull, myw[1], c0 + e, G);
+                            const float w2 = __shfl_sync(kFull, myw[2], c0 + e, G);
+                            const float w3 = __shfl_sync(kFull, myw[3], c0 + e, G);
                             float gv[VEC];
                             unpack_row<T, VEC>(raw[e], gv);
                             constexpr bool PK = use_packed_fma<T, 2>();
@@ -874,8 +894,7 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                             }
                         }
                     }
-                    if (!more) break;
-                    e0 += G;
+                    if (GW > 1 ? !__any_sync(kFull, active) : !active) break;
                 }
                 if (dense) {
                     // fixed-order combine over the GW groups of the warp (lane bits >= log2 G)
@@ -883,10 +902,10 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                     for (int d = G; d < 32; d <<= 1) {
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
-                            acc.g1[i] += __shfl_xor_sync(0xffffffffu, acc.g1[i], d);
-                            acc.g2[i] += __shfl_xor_sync(0xffffffffu, acc.g2[i], d);
-                            acc.g3[i] += __shfl_xor_sync(0xffffffffu, acc.g3[i], d);
-                            acc.g4[i] += __shfl_xor_sync(0xffffffffu, acc.g4[i], d);
+                            acc.g1[i] += __shfl_xor_sync(kFull, acc.g1[i], d);
+                            acc.g2[i] += __shfl_xor_sync(kFull, acc.g2[i], d);
+                            acc.g3[i] += __shfl_xor_sync(kFull, acc.g3[i], d);
+                            acc.g4[i] += __shfl_xor_sync(kFull, acc.g4[i], d);
                         }
                     }
                 }
