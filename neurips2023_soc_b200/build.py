@@ -69,6 +69,8 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: P
                           *map(str, objs)], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    if variant:
+        shutil.rmtree(objdir, ignore_errors=True)      # a variant's objects are never reused
     return out
 
 

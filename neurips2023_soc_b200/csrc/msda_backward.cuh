@@ -301,9 +301,8 @@ __global__ void __launch_bounds__(kThreads, MSDA_BWD_MIN_BLOCKS) msda_bwd_sample
         if constexpr (CHAIN) {
             // softmax backward: the lanes that wrote a sample's d/d weight come back to it once the (query, head)'s
             // sum is known (their own stores, re-read in program order)
-            const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 #pragma unroll
-            for (int dd = 1; dd < G; dd <<= 1) chain_dot += __shfl_xor_sync(gmask, chain_dot, dd, G);
+            for (int dd = 1; dd < G; dd <<= 1) chain_dot += __shfl_xor_sync(0xffffffffu, chain_dot, dd, G);   // all lanes are here
 #pragma unroll 1
             for (int lc = 0; lc < LPC; ++lc) {
                 if (l0 + lc >= p.L) break;
@@ -1028,16 +1027,18 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
             const T* __restrict__ vb = static_cast<const T*>(p.value) + ((size_t)n * p.S * p.M + m) * p.D + gl * VEC;
             TA* __restrict__ gloc = static_cast<TA*>(p.grad_loc);
             TA* __restrict__ gattn = static_cast<TA*>(p.grad_attn);
-            const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
             if (staged) __syncthreads();                        // s_g of this (frame, head) is complete
-            for (int i = grp; i < nsamp; i += NG) {
-                const int q = i / p.P, pt = i - q * p.P;
+            // (the groups of a warp take the loop together: the reduction below runs with every lane present)
+            for (int i0 = 0; i0 < nsamp; i0 += NG) {
+                const int i = i0 + grp;
+                const bool mine = i < nsamp;
+                const int q = mine ? i / p.P : 0, pt = mine ? i - q * p.P : 0;
                 const size_t si = (((size_t)n * p.Lq + q) * p.M + m) * p.LP + l * p.P + pt;
                 const XY<float> xy = load_xy(loc + 2 * si);
                 const float a = (float)ld_stream(attn + si);
                 const Sample<float> sm = locate(xy.x, xy.y, L_.H, L_.W);
                 float ga = 0.f, gx = 0.f, gy = 0.f;
-                if (sm.ok) {                                     // uniform over the lane group
+                if (mine && sm.ok) {                             // uniform over the lane group
                     int pix[4];
                     corner_pixels(sm, L_, pix);
                     float v[4][VEC], g[VEC];
@@ -1060,14 +1061,14 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                         gx = fmaf(g[c], hh * (v[1][c] - v[0][c]) + sm.lh * (v[3][c] - v[2][c]), gx);
                         gy = fmaf(g[c], hw * (v[2][c] - v[0][c]) + sm.lw * (v[3][c] - v[1][c]), gy);
                     }
-#pragma unroll
-                    for (int d = 1; d < G; d <<= 1) {
-                        ga += __shfl_xor_sync(gmask, ga, d, G);
-                        gx += __shfl_xor_sync(gmask, gx, d, G);
-                        gy += __shfl_xor_sync(gmask, gy, d, G);
-                    }
                 }
-                if (gl == 0) {
+#pragma unroll
+                for (int d = 1; d < G; d <<= 1) {
+                    ga += __shfl_xor_sync(0xffffffffu, ga, d, G);
+                    gx += __shfl_xor_sync(0xffffffffu, gx, d, G);
+                    gy += __shfl_xor_sync(0xffffffffu, gy, d, G);
+                }
+                if (mine && gl == 0) {
                     gattn[si] = Elem<TA>::from_f(ga);
                     store_xy(gloc + 2 * si, (float)L_.W * a * gx, (float)L_.H * a * gy);
                 }

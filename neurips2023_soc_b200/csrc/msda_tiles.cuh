@@ -94,18 +94,19 @@ __device__ __forceinline__ void fused_prologue(Staged<TileShape<G>::DPT>& st, co
     const int st_s = threadIdx.x % kSC;
     const int sg = w.c0 + st_s;
     const Level L_ = lv[min(sg / P, p.L - 1)];
-    const uint32_t hmask = 0xffffu << (threadIdx.x & 16);
+    // (every thread of the CTA stages: the warp is converged here, and stays so -- the skip below is warp-wide)
+    constexpr uint32_t kFull = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < DPT; ++k) {
         const bool live = st.q[k] >= 0;                  // false for empty rows and for slots past L*P
-        if (__ballot_sync(hmask, live) == 0) continue;   // empty row: uniform over its 16 lanes
+        if (!__any_sync(kFull, live)) continue;          // both rows of the warp are empty
         float m = live ? st.a[k] : -INFINITY;
 #pragma unroll
-        for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(hmask, m, d, 16));
+        for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, d, 16));
         const float e = live ? expf(st.a[k] - m) : 0.f;
         float sum = e;
 #pragma unroll
-        for (int d = 8; d > 0; d >>= 1) sum += __shfl_xor_sync(hmask, sum, d, 16);
+        for (int d = 8; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d, 16);
         if (live) {
             st.a[k] = e / sum;
             st.x[k] = st.rx[k] + st.x[k] / (float)L_.W;

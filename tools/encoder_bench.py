@@ -186,7 +186,7 @@ def main():
         print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "encoder": which, "layers": a.layers, "frames_per_gpu": a.frames,
                           "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "cuda_graph": a.graph, "n_gpus": world, "ms_per_step": float(ms.item()),
                           "queries_per_s": world * a.frames * S / (float(ms.item()) * 1e-3),
-                          "msda_kernels_ms_per_step": fwd_ms, "loss": float(loss)}))
+                          "msda_kernels_ms_per_step": fwd_ms, "loss": float(loss.detach())}))
     if world > 1:
         dist.destroy_process_group()
 
