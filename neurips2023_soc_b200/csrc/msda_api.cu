@@ -860,6 +860,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
         pl.tile = false;
     if (pl.tile && (long long)S + 65536 >= (1LL << 28)) pl.tile = false;
     if (pl.tile && (long long)S * M * D * (long long)dtype_size(value_dtype) >= (1LL << 31)) pl.tile = false;  // signed 32-bit byte offsets
+    if (pl.tile && (long long)N * M * Lq * LP >= (1LL << 32)) pl.tile = false;     // the walker's 32-bit entry positions
     if (chain) {
         if (!(pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16)) || LP > kSC ||
             (flags & (MSDA_FLAG_ATOMIC_GRAD_VALUE | MSDA_FLAG_GENERIC)))

@@ -688,11 +688,11 @@ struct BinAcc {
     }
 };
 
-__device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restrict__ ent, uint32_t pos, uint32_t end) {
+__device__ __forceinline__ Entry<float> load_entry(const Entry<float>* __restrict__ ent, uint32_t base, uint32_t pos, uint32_t end) {
     Entry<float> e;
     e.id = 0; e.lh = e.lw = e.a = 0.f;
     if (pos < end) {
-        const uint4 t = ld_stream_b128(ent + pos);
+        const uint4 t = ld_stream_b128(ent + (size_t)(base + pos));
         e.id = t.x; e.lh = __uint_as_float(t.y); e.lw = __uint_as_float(t.z); e.a = __uint_as_float(t.w);
     }
     return e;
@@ -749,8 +749,9 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
     __shared__ int s_sb, s_sq;
     __shared__ int tstart[kMaxLevels + 1];   // first tile of each level in the launch-wide order
     __shared__ int s_tile;
-    __shared__ __align__(16) float sT[TH * TW * D];
-    __shared__ __align__(16) float sB[TH * TW * D];
+    __shared__ __align__(16) float sTB[2 * TH * TW * D];      // T tile, then B tile: one base, constant distance
+    float* const sT = sTB;
+    float* const sB = sTB + TH * TW * D;
     load_levels(p, lv, &s_sb, &s_sq);
     auto is_dense = [&](const int l) { return GW > 1 && lv[l].nch_log2 >= 3; };
     auto tiles_of = [&](const int l) {
@@ -778,6 +779,7 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
     const int total_tiles = tstart[p.L];
     const size_t per_nm = (size_t)p.Lq * p.LP;
     const size_t qstride = (size_t)p.M * p.D;
+    const uint32_t rowbytes = (uint32_t)(qstride * sizeof(T));     // < 2^31 (tile path: msda_api.cu)
 
     while (true) {
         // dynamic tile scheduler: heavy tiles first, no CTA is handed two of them while others idle
@@ -801,8 +803,12 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
 
         const size_t nm = (size_t)n * p.M + m;
         const uint32_t* off = p.bin_off + nm * (p.sb_max + 1);
-        const Entry<float>* ent = entries + nm * per_nm;
-        const T* gbase = gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC;
+        // entries are addressed from the launch-wide base with a 32-bit position (N*M*Lq*L*P < 2^32, msda_api.cu): one
+        // register instead of a pointer ptxas would rather recompute than keep
+        const Entry<float>* const ent = entries;
+        const uint32_t ebase = (uint32_t)(nm * per_nm);
+        // rows of grad_output by byte offset: query * rowbytes is a 32 x 32 -> 64 bit multiply-add onto the base
+        const char* gbase = reinterpret_cast<const char*>(gout + ((size_t)n * p.Lq * p.M + m) * p.D + gl * VEC);
 
         // The lane groups of a warp run every loop below in lockstep, whatever their own rows and bins hold: trip
         // counts are warp-wide (votes), a group with nothing left works on empty batches (zero weights, no loads).
@@ -818,8 +824,11 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
             if (GW > 1 ? !__any_sync(kFull, live) : !live) continue;   // no group of the warp has one
             const bool emit_t = live && row >= 1;                      // pixel row by-1 is in the tile
             const bool emit_b = live && row <= th_l - 1 && by <= L_.H - 1;     // pixel row by is in the tile
-            float* const tdst = sT + (row - 1) * TW * D + gl * VEC;
-            float* const bdst = sB + row * TW * D + gl * VEC;
+            // emit pointer: T[row-1][b-1] of this lane, advanced by one pixel per bin; B[row][b-1] sits at a constant
+            // distance from it (kept as ONE running register: ptxas otherwise rebuilds both addresses from the thread
+            // index at every bin)
+            constexpr int kTtoB = TH * TW * D + TW * D;
+            float* tcur = sT + (row - 1) * TW * D + gl * VEC - D;
 
             // Entry offsets at the bin boundaries of the row segment, read one bin ahead.
             const uint32_t* orow = off + L_.bin_start + (((live ? by : y0) * (L_.W + 1) + x0) << L_.nch_log2);
@@ -842,7 +851,7 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
             uint32_t r0, r1, n0, n1;
             share(b_lo, b_hi, r0, r1);
             share(b_hi, b_nx, n0, n1);
-            Entry<float> nxt = load_entry(ent, r0 + gl, r1);
+            Entry<float> nxt = load_entry(ent, ebase, r0 + gl, r1);
 
 #pragma unroll 1
             for (int b = 0; b < nb; ++b) {
@@ -856,7 +865,7 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                     if (active) {
                         mine = nxt;
                         const bool more = e0 + G < r1;
-                        nxt = more ? load_entry(ent, e0 + G + gl, r1) : load_entry(ent, n0 + gl, n1);
+                        nxt = more ? load_entry(ent, ebase, e0 + G + gl, r1) : load_entry(ent, ebase, n0 + gl, n1);
                         nbat = e0 < r1 ? (int)min((uint32_t)G, r1 - e0) : 0;
                         active = more;
                         e0 += G;
@@ -873,7 +882,7 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                         for (int e = 0; e < STEP; ++e) {
                             const uint32_t q = __shfl_sync(kFull, myq, c0 + e, G);
                             // entries past nbat carry zero weights and zero rows
-                            raw[e] = load_raw_if<T, VEC>(c0 + e < nbat, gbase + (size_t)q * qstride);
+                            raw[e] = load_raw_if<T, VEC>(c0 + e < nbat, reinterpret_cast<const T*>(gbase + (size_t)q * rowbytes));
                         }
 #pragma unroll
                         for (int e = 0; e < STEP; ++e) {
@@ -912,13 +921,14 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                 if (b > 0 && (!dense || gw == 0)) {
                     if (emit_t) {
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) tdst[(b - 1) * D + i] = acc.g1[i] + p2[i];
+                        for (int i = 0; i < VEC; ++i) tcur[i] = acc.g1[i] + p2[i];
                     }
                     if (emit_b) {
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) bdst[(b - 1) * D + i] = acc.g3[i] + p4[i];
+                        for (int i = 0; i < VEC; ++i) tcur[kTtoB + i] = acc.g3[i] + p4[i];
                     }
                 }
+                tcur += D;
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) { p2[i] = acc.g2[i]; p4[i] = acc.g4[i]; }
                 acc.clear();
