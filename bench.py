@@ -513,7 +513,7 @@ def run_ours(args):
 
     # the host entry point: frames streamed in chunks, H2D / kernels / D2H on three streams
     from neurips2023_soc_b200.host_frames import HostFramePipeline
-    pipe = HostFramePipeline(dev, frames_per_chunk=min(args.e2e_frames_per_chunk, N))
+    pipe = HostFramePipeline(dev, frames_per_chunk=min(args.e2e_frames_per_chunk, N), graph=args.e2e_graph)
     results = (res_host["out"], res_host["gv"], res_host["gl"], res_host["ga"])
 
     def e2e_step():
@@ -551,7 +551,8 @@ def run_ours(args):
     e2e = {"value": total_queries / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
            "api": f"HostFramePipeline.forward_backward: pinned host buffers, chunks of up to {pipe.frames_per_chunk} "
-                  f"frames (short first and last chunks), H2D / kernels / D2H pipelined on three streams ({pipe.launches} kernel launches per step)",
+                  f"frames (short first and last chunks), H2D / kernels / D2H pipelined on three streams ({pipe.launches} kernel launches per step)"
+                  + (", the step replayed as one CUDA graph" if pipe.graph else ", enqueued call by call"),
            "one_stream_ms_per_step": e2e_serial_ms,
            "pcie_GBs_each_way": max(h2d, d2h) / (e2e_ms * 1e-3) / 1e9,
            "host_copy_ceiling": {"what": "the step's bytes as bare pinned copies, H2D and D2H at once, all ranks at once "
@@ -606,6 +607,8 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock bound of the whole run; steps shrink to fewer frames beyond it")
     ap.add_argument("--e2e-frames-per-chunk", type=int, default=4)
+    ap.add_argument("--e2e-graph", action="store_true",
+                    help="replay the host pipeline's step as one CUDA graph (measured: no faster -- the copies bound it)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

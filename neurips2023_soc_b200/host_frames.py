@@ -75,19 +75,27 @@ class HostFramePipeline:
         out, grad_value, grad_loc, grad_attn = pipe.forward_backward(
             value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output)
 
+    ``graph=True`` replays a captured CUDA graph of the step when it is called again with the same host buffers.
+
     All six tensors except the two small int64 ones are pinned host tensors with the layouts of
     ``MSDeformAttnFunction``; the four results are pinned host tensors (pass ``results=`` to reuse
     buffers).  The call returns once everything is queued; the results are complete after the current
     stream (which is made to wait for the pipeline) has been synchronised.
     """
 
-    def __init__(self, device="cuda:0", frames_per_chunk: int = 4, im2col_step: int = 64, ramp: bool = True):
+    def __init__(self, device="cuda:0", frames_per_chunk: int = 4, im2col_step: int = 64, ramp: bool = True,
+                 graph: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("HostFramePipeline needs a CUDA device: there is no CPU path for the op")
         self.device = torch.device(device)
         self.frames_per_chunk = int(frames_per_chunk)
         self.im2col_step = im2col_step
         self.ramp = ramp
+        # graph=True: the whole step (every copy and launch of every chunk, with the cross-stream ordering) is captured
+        # once per set of host buffers and replayed with ONE launch afterwards -- no per-chunk host work, so the copy
+        # engines are never left waiting for the next enqueue.  Calls with other buffers capture their own graph.
+        self.graph = bool(graph)
+        self._graphs: Dict[Tuple, "torch.cuda.CUDAGraph"] = {}
         self.trace = False                     # True: time every stage of the next call with CUDA events
         self._marks: List[Tuple[int, str, torch.cuda.Event, torch.cuda.Event]] = []
         self._t0: Optional[torch.cuda.Event] = None
@@ -156,66 +164,88 @@ class HostFramePipeline:
         slots = self._staging(named)
 
         with torch.cuda.device(self.device):
-            caller = torch.cuda.current_stream()
-            start = torch.cuda.Event(enable_timing=self.trace)
-            start.record(caller)
-            self._marks, self._t0 = [], start
-
-            def mark(stream):
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(stream)
-                return e
-            self.s_in.wait_event(start)        # host buffers written by work queued on the caller's stream
-            self.s_out.wait_event(start)       # ... and result buffers it may still be reading
-            self.launches = 0
-            last_out = None
-            plan = (ramped_chunk_ranges if self.ramp else chunk_ranges)(N, self.frames_per_chunk)
-            for i, (lo, hi) in enumerate(plan):
-                k = i % _SLOTS
-                slot = slots[k]
-                n = hi - lo
-                if self._computed[k] is not None:
-                    self.s_in.wait_event(self._computed[k])
-                b0 = mark(self.s_in) if self.trace else None
-                with torch.cuda.stream(self.s_in):
-                    for name, t in named:
-                        slot[name][:n].copy_(t[lo:hi], non_blocking=True)
-                if self.trace:
-                    self._marks.append((i, "h2d", b0, mark(self.s_in)))
-                ready = torch.cuda.Event()
-                ready.record(self.s_in)
-                self.s_run.wait_event(ready)
-                if self._drained[k] is not None:
-                    self.s_run.wait_event(self._drained[k])
-                b0 = mark(self.s_run) if self.trace else None
-                with torch.cuda.stream(self.s_run):
-                    a = (slot["value"][:n], shapes_d, lsi_d, slot["sampling_locations"][:n], slot["attention_weights"][:n])
-                    _, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True,
-                                                               out=slot["out"][:n], index_buf=slot["index"])   # None for small calls
-                    self.launches += msda_ext.last_launch_count()
-                    msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index,
-                                                     grads=(slot["gv"][:n], slot["gl"][:n], slot["ga"][:n]),
-                                                     workspace=slot["ws"])
-                    self.launches += msda_ext.last_launch_count()
-                if self.trace:
-                    self._marks.append((i, "run", b0, mark(self.s_run)))
-                done = torch.cuda.Event()
-                done.record(self.s_run)
-                self._computed[k] = done
-                self.s_out.wait_event(done)
-                b0 = mark(self.s_out) if self.trace else None
-                with torch.cuda.stream(self.s_out):
-                    for dst, src in ((out_h, "out"), (gv_h, "gv"), (gl_h, "gl"), (ga_h, "ga")):
-                        dst[lo:hi].copy_(slot[src][:n], non_blocking=True)
-                if self.trace:
-                    self._marks.append((i, "d2h", b0, mark(self.s_out)))
-                last_out = torch.cuda.Event()
-                last_out.record(self.s_out)
-                self._drained[k] = last_out
-            if last_out is not None:
-                caller.wait_event(last_out)    # synchronising the caller's stream now covers the whole pipeline
+            if not self.graph or self.trace:
+                self._enqueue(named, results, shapes_d, lsi_d, slots, N)
+            else:
+                key = tuple(t.data_ptr() for _, t in named) + tuple(r.data_ptr() for r in results) + \
+                    (N, self._slot_key, shapes_d.data_ptr(), lsi_d.data_ptr())
+                g = self._graphs.get(key)
+                if g is None:
+                    self._enqueue(named, results, shapes_d, lsi_d, slots, N)      # warm-up (and this call's results)
+                    torch.cuda.synchronize(self.device)
+                    self._computed, self._drained = [None] * _SLOTS, [None] * _SLOTS   # no events from outside the capture
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=torch.cuda.Stream()):
+                        self._enqueue(named, results, shapes_d, lsi_d, slots, N)
+                    self._computed, self._drained = [None] * _SLOTS, [None] * _SLOTS   # replays are ordered on the caller's stream
+                    self._graphs[key] = g
+                else:
+                    g.replay()
         return out_h, gv_h, gl_h, ga_h
 
+
+    def _enqueue(self, named, results, shapes_d, lsi_d, slots, N):
+        """Queue one step: every chunk's copy-in, kernels and copy-out on the three streams, ordered by events; the
+        caller's (current) stream waits for the last copy-out.  Also what a CUDA graph of the step captures."""
+        out_h, gv_h, gl_h, ga_h = results
+        caller = torch.cuda.current_stream()
+        start = torch.cuda.Event(enable_timing=self.trace)
+        start.record(caller)
+        self._marks, self._t0 = [], start
+
+        def mark(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
+        self.s_in.wait_event(start)        # host buffers written by work queued on the caller's stream
+        self.s_out.wait_event(start)       # ... and result buffers it may still be reading
+        self.launches = 0
+        last_out = None
+        plan = (ramped_chunk_ranges if self.ramp else chunk_ranges)(N, self.frames_per_chunk)
+        for i, (lo, hi) in enumerate(plan):
+            k = i % _SLOTS
+            slot = slots[k]
+            n = hi - lo
+            if self._computed[k] is not None:
+                self.s_in.wait_event(self._computed[k])
+            b0 = mark(self.s_in) if self.trace else None
+            with torch.cuda.stream(self.s_in):
+                for name, t in named:
+                    slot[name][:n].copy_(t[lo:hi], non_blocking=True)
+            if self.trace:
+                self._marks.append((i, "h2d", b0, mark(self.s_in)))
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+            self.s_run.wait_event(ready)
+            if self._drained[k] is not None:
+                self.s_run.wait_event(self._drained[k])
+            b0 = mark(self.s_run) if self.trace else None
+            with torch.cuda.stream(self.s_run):
+                a = (slot["value"][:n], shapes_d, lsi_d, slot["sampling_locations"][:n], slot["attention_weights"][:n])
+                _, index = msda_ext.ms_deform_attn_forward(*a, self.im2col_step, want_index=True,
+                                                           out=slot["out"][:n], index_buf=slot["index"])   # None for small calls
+                self.launches += msda_ext.last_launch_count()
+                msda_ext.ms_deform_attn_backward(*a, slot["grad_output"][:n], self.im2col_step, index=index,
+                                                 grads=(slot["gv"][:n], slot["gl"][:n], slot["ga"][:n]),
+                                                 workspace=slot["ws"])
+                self.launches += msda_ext.last_launch_count()
+            if self.trace:
+                self._marks.append((i, "run", b0, mark(self.s_run)))
+            done = torch.cuda.Event()
+            done.record(self.s_run)
+            self._computed[k] = done
+            self.s_out.wait_event(done)
+            b0 = mark(self.s_out) if self.trace else None
+            with torch.cuda.stream(self.s_out):
+                for dst, src in ((out_h, "out"), (gv_h, "gv"), (gl_h, "gl"), (ga_h, "ga")):
+                    dst[lo:hi].copy_(slot[src][:n], non_blocking=True)
+            if self.trace:
+                self._marks.append((i, "d2h", b0, mark(self.s_out)))
+            last_out = torch.cuda.Event()
+            last_out.record(self.s_out)
+            self._drained[k] = last_out
+        if last_out is not None:
+            caller.wait_event(last_out)    # synchronising the caller's stream now covers the whole pipeline
 
     def timeline(self) -> List[Tuple[int, str, float, float]]:
         """(chunk, stage, begin ms, end ms) of the last traced call, relative to its start on the caller's

@@ -489,6 +489,42 @@ def test_host_frame_pipeline_matches_one_call(frames_per_chunk, ramp):
         pipe.forward_backward(host.value, host.spatial_shapes, host.level_start_index, pins[1], pins[2], pins[3])
 
 
+def test_host_frame_pipeline_as_cuda_graph():
+    """graph=True: the step is captured once per set of host buffers and replayed; every call (the capturing one,
+    replays, replays after the inputs changed in place, another set of buffers) returns the bits of one call."""
+    from neurips2023_soc_b200.host_frames import HostFramePipeline
+    x = make_inputs(N=7, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], dist="encoder", seed=12)
+    host = x.to("cpu", torch.bfloat16, torch.float32)
+    pins = [t.pin_memory() for t in (host.value, host.sampling_locations, host.attention_weights, host.grad_output)]
+
+    def reference():
+        d = [p.to(DEV) for p in pins]
+        sh, ls = host.spatial_shapes.to(DEV), host.level_start_index.to(DEV)
+        out, index = msda_ext.ms_deform_attn_forward(d[0], sh, ls, d[1], d[2], 64, want_index=True)
+        return [out] + msda_ext.ms_deform_attn_backward(d[0], sh, ls, d[1], d[2], d[3], 64, index=index)
+
+    pipe = HostFramePipeline(DEV, frames_per_chunk=2, graph=True)
+    results = None
+    for it in range(4):
+        if it == 2:                                    # new contents in the same host buffers: the replay must see them
+            pins[0].mul_(0.5)
+            pins[3].add_(0.25)
+        ref = reference()
+        res = pipe.forward_backward(pins[0], host.spatial_shapes, host.level_start_index, pins[1], pins[2], pins[3],
+                                    results=results)
+        torch.cuda.current_stream().synchronize()
+        results = res
+        for got, want in zip(res, ref):
+            assert torch.equal(got, want.cpu())
+    assert len(pipe._graphs) == 1
+    other = [p.clone().pin_memory() for p in pins]     # other buffers: their own graph
+    res2 = pipe.forward_backward(other[0], host.spatial_shapes, host.level_start_index, other[1], other[2], other[3])
+    torch.cuda.current_stream().synchronize()
+    for got, want in zip(res2, reference()):
+        assert torch.equal(got, want.cpu())
+    assert len(pipe._graphs) == 2
+
+
 @pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
                                       (torch.bfloat16, torch.bfloat16)])
 @pytest.mark.parametrize("kw", [dict(N=3, dist="decoder", Lq=20), dict(N=2, dist="decoder", Lq=5),
