@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of kernel-variant builds (variants/*.so, tools/build_variant.sh): per-kernel times of one forward + backward
-# usage: tools/r2_ab.sh <variant names or "default"> ...   (env DTYPES="bf16mix fp32")
+# usage: tools/ab_variants.sh <variant names or "default"> ...   (env DTYPES="bf16mix fp32")
 mkdir -p gpurun_out
 cd ${GRAFT_REPO_ROOT:-.}
 for lib in "$@"; do
