@@ -62,7 +62,7 @@
 extern "C" {
 #endif
 
-#define MSDA_VERSION 100 /* major*100 + minor */
+#define MSDA_VERSION 101 /* major*100 + minor */
 
 enum msda_dtype { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F16 = 2, MSDA_F64 = 3 };
 
@@ -142,10 +142,14 @@ int msda_backward_indexed(const void *value, const int64_t *spatial_shapes, cons
  * reference_points [N][Lq][L][2] fp32; sampling_offsets [N][Lq][M][L][P][2] and attn_logits
  * [N][Lq][M][L*P] in in_dtype (the value dtype or F32); the two results are written as fp32 to
  * sampling_loc_out / attn_weight_out (the module returns them, the backward reads them).
+ * value_padding_mask (may be NULL): [N][S] bytes, non-zero on padded pixels -- the module's
+ *   value = value.masked_fill(input_padding_mask[..., None], 0)      (ms_deform_attn.py:96-97)
+ * without the pass over `value`: a padded pixel's row counts as zero wherever a sample touches it, and the backward
+ * (which must be given the same mask) leaves its grad_value row zero.
  * Tile-kernel shapes with L*P <= 16 only: anything else returns MSDA_ERR_UNSUPPORTED and the caller
  * keeps the unfused sequence.  `index` as in msda_forward_indexed (may be NULL). */
 int msda_forward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                       const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                       const unsigned char *value_padding_mask, const void *reference_points, const void *sampling_offsets, const void *attn_logits,
                        void *output, void *sampling_loc_out, void *attn_weight_out,
                        void *index, size_t index_bytes,
                        int N, int S, int M, int D, int L, int Lq, int P,
@@ -159,7 +163,7 @@ int msda_forward_fused(const void *value, const int64_t *spatial_shapes, const i
  * needed, is the sum of grad_sampling_offsets * (W_l, H_l) over heads and points.)  Same shape support as
  * msda_forward_fused; anything else returns MSDA_ERR_UNSUPPORTED. */
 int msda_backward_fused(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                        const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                        const unsigned char *value_padding_mask, const void *sampling_loc, const void *attn_weight, const void *grad_output,
                         void *grad_value, void *grad_sampling_offsets, void *grad_attn_logits,
                         void *workspace, size_t workspace_bytes, void *index, size_t index_bytes,
                         int N, int S, int M, int D, int L, int Lq, int P,
@@ -173,7 +177,7 @@ int msda_backward_fused(const void *value, const int64_t *spatial_shapes, const 
  * fp32 round trip of 384 values per query).  Needs the index the forward left (index != NULL); only for calls that
  * keep one (msda_index_bytes != 0). */
 int msda_backward_fused_raw(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                            const void *reference_points, const void *sampling_offsets, const void *attn_logits,
+                            const unsigned char *value_padding_mask, const void *reference_points, const void *sampling_offsets, const void *attn_logits,
                             const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attn_logits,
                             void *workspace, size_t workspace_bytes, void *index, size_t index_bytes,
                             int N, int S, int M, int D, int L, int Lq, int P,

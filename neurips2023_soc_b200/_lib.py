@@ -62,13 +62,13 @@ def load() -> ctypes.CDLL:
     lib.msda_forward_indexed.restype = i
     lib.msda_forward_indexed.argtypes = [vp] * 7 + [sz] + dims + [i, i, i, vp, u]
     lib.msda_forward_fused.restype = i
-    lib.msda_forward_fused.argtypes = [vp] * 10 + [sz] + dims + [i, i, i, vp, u]
+    lib.msda_forward_fused.argtypes = [vp] * 11 + [sz] + dims + [i, i, i, vp, u]
     lib.msda_backward_indexed.restype = i
     lib.msda_backward_indexed.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     lib.msda_backward_fused.restype = i
-    lib.msda_backward_fused.argtypes = [vp] * 10 + [sz, vp, sz] + dims + [i, i, i, vp, u]
+    lib.msda_backward_fused.argtypes = [vp] * 11 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     lib.msda_backward_fused_raw.restype = i
-    lib.msda_backward_fused_raw.argtypes = [vp] * 11 + [sz, vp, sz] + dims + [i, i, i, vp, u]
+    lib.msda_backward_fused_raw.argtypes = [vp] * 12 + [sz, vp, sz] + dims + [i, i, i, vp, u]
     ll, fl, fp = ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
     lib.msda_add_layernorm_forward.restype = i
     lib.msda_add_layernorm_forward.argtypes = [vp] * 8 + [ll, i, i, fl, vp]

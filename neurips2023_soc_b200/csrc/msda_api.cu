@@ -679,7 +679,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
                         const void* sampling_loc, const void* attn_weight, void* output, void* index,
                         size_t index_size, const void* reference_points, void* loc_out, void* attn_out, int N, int S,
                         int M, int D, int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step,
-                        void* cuda_stream, unsigned flags) {
+                        void* cuda_stream, unsigned flags, const void* value_mask = nullptr) {
     msda_host::g_launches.store(0);
     const msda_host::DeviceGuard guard(value);   // the device that owns `value` is current for this call
     const bool fused = reference_points != nullptr;
@@ -702,6 +702,7 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
     p.loc = sampling_loc; p.attn = attn_weight; p.out = output;
     p.ref = static_cast<const float*>(reference_points);
     p.loc_out = static_cast<float*>(loc_out); p.attn_out = static_cast<float*>(attn_out);
+    p.value_mask = static_cast<const uint8_t*>(value_mask);
     p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = L * P;
     p.id_shift = id_shift_for(p.LP);
     p.flags = flags;
@@ -728,6 +729,8 @@ static int forward_impl(const void* value, const int64_t* spatial_shapes, const 
     const bool tile = pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16);
     if (fused && !(tile && aligned16(reference_points) && aligned16(loc_out) && aligned16(attn_out)))   /* null is aligned */
         return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue exists for the tile kernels only (fp32/bf16, D and P as in DESIGN.md)");
+    if (value_mask && (!tile || (flags & MSDA_FLAG_GENERIC)))
+        return fail(MSDA_ERR_UNSUPPORTED, "the padding mask is applied by the tile kernels only");
     switch (value_dtype) {
         case MSDA_F32:
             rc = tile ? dispatch_fwd_tile<float>(p, pl, value_dtype, st) : launch_fwd_generic<float, float, float>(p, st);
@@ -767,14 +770,14 @@ int msda_forward_indexed(const void* value, const int64_t* spatial_shapes, const
 }
 
 int msda_forward_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                       const void* reference_points, const void* sampling_offsets, const void* attn_logits,
+                       const unsigned char* value_padding_mask, const void* reference_points, const void* sampling_offsets, const void* attn_logits,
                        void* output, void* sampling_loc_out, void* attn_weight_out, void* index, size_t index_size,
                        int N, int S, int M, int D, int L, int Lq, int P, int value_dtype, int in_dtype,
                        int im2col_step, void* cuda_stream, unsigned flags) {
     if (!reference_points) return fail(MSDA_ERR_INVALID_ARGUMENT, "null reference_points");
     return forward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, output, index,
                         index_size, reference_points, sampling_loc_out, attn_weight_out, N, S, M, D, L, Lq, P,
-                        value_dtype, in_dtype, im2col_step, cuda_stream, flags);
+                        value_dtype, in_dtype, im2col_step, cuda_stream, flags, value_padding_mask);
 }
 
 int msda_forward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
@@ -804,7 +807,8 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                          size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
                          int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
-                         unsigned flags, bool chain, const void* reference_points = nullptr) {
+                         unsigned flags, bool chain, const void* reference_points = nullptr,
+                         const void* value_mask = nullptr) {
     msda_host::g_launches.store(0);
     const msda_host::DeviceGuard guard(value);   // the device that owns `value` is current for this call
     flags &= ~(kFlagChain | kFlagDirectAll);
@@ -840,6 +844,7 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
     p.loc = sampling_loc; p.attn = attn_weight; p.grad_out = grad_output;
     p.grad_value = grad_value; p.grad_loc = grad_sampling_loc; p.grad_attn = grad_attn_weight;
     p.ref = static_cast<const float*>(reference_points);     // raw-input chain variant only
+    p.value_mask = static_cast<const uint8_t*>(value_mask);
     p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P; p.LP = LP;
     p.id_shift = shift;
     p.sb_max = w.sb_max; p.big_cap = w.big_cap;
@@ -867,6 +872,9 @@ static int backward_impl(const void* value, const int64_t* spatial_shapes, const
             return fail(MSDA_ERR_UNSUPPORTED, "the fused prologue exists for the tile kernels only (fp32/bf16, D and P as in DESIGN.md, L*P <= %d)", kSC);
         p.flags |= kFlagChain;
     }
+    if (value_mask && (!(pl.tile && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16)) ||
+                       (flags & (MSDA_FLAG_ATOMIC_GRAD_VALUE | MSDA_FLAG_GENERIC | MSDA_FLAG_BIN_KERNEL))))
+        return fail(MSDA_ERR_UNSUPPORTED, "the padding mask is applied by the tile kernels only (default grad_value path)");
 
     const bool aux32 = aux_dtype == MSDA_F32;
     switch (value_dtype) {
@@ -893,18 +901,18 @@ int msda_backward_indexed(const void* value, const int64_t* spatial_shapes, cons
 }
 
 int msda_backward_fused(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                        const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                        const unsigned char* value_padding_mask, const void* sampling_loc, const void* attn_weight, const void* grad_output,
                         void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* workspace,
                         size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M, int D,
                         int L, int Lq, int P, int value_dtype, int aux_dtype, int im2col_step, void* cuda_stream,
                         unsigned flags) {
     return backward_impl(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, grad_value,
                          grad_sampling_offsets, grad_attn_logits, workspace, workspace_bytes, index, index_size, N, S, M,
-                         D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags, true);
+                         D, L, Lq, P, value_dtype, aux_dtype, im2col_step, cuda_stream, flags, true, nullptr, value_padding_mask);
 }
 
 int msda_backward_fused_raw(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                            const void* reference_points, const void* sampling_offsets, const void* attn_logits,
+                            const unsigned char* value_padding_mask, const void* reference_points, const void* sampling_offsets, const void* attn_logits,
                             const void* grad_output, void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
                             void* workspace, size_t workspace_bytes, void* index, size_t index_size, int N, int S, int M,
                             int D, int L, int Lq, int P, int value_dtype, int in_dtype, int im2col_step, void* cuda_stream,
@@ -917,7 +925,8 @@ int msda_backward_fused_raw(const void* value, const int64_t* spatial_shapes, co
         return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_backward_fused_raw needs the index the matching msda_forward_fused left");
     return backward_impl(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, grad_output, grad_value,
                          grad_sampling_offsets, grad_attn_logits, workspace, workspace_bytes, index, index_size, N, S, M, D,
-                         L, Lq, P, value_dtype, in_dtype, im2col_step, cuda_stream, flags, true, reference_points);
+                         L, Lq, P, value_dtype, in_dtype, im2col_step, cuda_stream, flags, true, reference_points,
+                         value_padding_mask);
 }
 
 int msda_backward_ex(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,

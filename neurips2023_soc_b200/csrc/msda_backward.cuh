@@ -945,9 +945,11 @@ __global__ void __launch_bounds__(kGThreads, (BRT ? MSDA_WALK_G4_MIN_BLOCKS : wa
                 float v[VEC];
                 const float* a = sT + (py * TW + px) * D + c * VEC;
                 const float* b = sB + (py * TW + px) * D + c * VEC;
+                const size_t pixel = (size_t)n * p.S + L_.start + y * L_.W + x;
+                const bool padded = p.value_mask != nullptr && p.value_mask[pixel] != 0;    // masked_fill's backward
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) v[j] = a[j] + b[j];
-                store_row<T, VEC>(gval + ((size_t)n * p.S + L_.start + y * L_.W + x) * qstride + (size_t)m * p.D + c * VEC, v);
+                for (int j = 0; j < VEC; ++j) v[j] = padded ? 0.f : a[j] + b[j];
+                store_row<T, VEC>(gval + pixel * qstride + (size_t)m * p.D + c * VEC, v);
             }
         }
         __syncthreads();
@@ -1051,6 +1053,11 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                 if (mine && sm.ok) {                             // uniform over the lane group
                     int pix[4];
                     corner_pixels(sm, L_, pix);
+                    if (p.value_mask != nullptr) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4)
+                            if (pix[c4] >= 0 && p.value_mask[(size_t)n * p.S + pix[c4]]) pix[c4] = -1;
+                    }
                     float v[4][VEC], g[VEC];
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
@@ -1097,6 +1104,11 @@ __global__ void __launch_bounds__(kThreads) msda_grad_value_direct_kernel(const 
                 if (sm.ok) {
                     int pix[4];
                     corner_pixels(sm, L_, pix);           // level_start + h*W + w, or -1 outside the map
+                    if (p.value_mask != nullptr) {         // padded pixels receive nothing (their rows stay zero)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (pix[c] >= 0 && p.value_mask[(size_t)n * p.S + pix[c]]) pix[c] = -1;
+                    }
                     const float hh = 1.f - sm.lh, hw = 1.f - sm.lw;
                     const float cw[4] = {hh * hw, hh * sm.lw, sm.lh * hw, sm.lh * sm.lw};
 #pragma unroll

@@ -41,6 +41,8 @@ struct Params {
     const void* attn;        // [N][Lq][M][L][P]
     const void* grad_out;    // [N][Lq][M*D]           (backward)
     // fused prologue (msda_tiles.cuh): loc/attn above then hold the raw sampling offsets / attention logits
+    const uint8_t* value_mask;  // [N][S] or null: non-zero = padded pixel, its value row counts as zero and its
+                                //   grad_value row is zero (value.masked_fill(mask, 0) of the module, ms_deform_attn.py:96-97)
     const float* ref;        // [N][Lq][L][2] reference points
     float* loc_out;          // [N][Lq][M][L][P][2]  sampling locations computed on the way
     float* attn_out;         // [N][Lq][M][L][P]     softmax of the logits
@@ -351,6 +353,16 @@ __device__ __forceinline__ void corner_pixels(const Sample<CT>& s, const Level& 
     pix[1] = (h0 && w1) ? base + 1 : -1;
     pix[2] = (h1 && w0) ? base + lv.W : -1;
     pix[3] = (h1 && w1) ? base + lv.W + 1 : -1;
+}
+
+// Padding mask (fused module prologue): drops the corners that sit on padded pixels.  `flags` holds the four
+// in-range bits (top-left, top-right, bottom-left, bottom-right); `mk` points at the mask byte of the top-left corner.
+__device__ __forceinline__ unsigned mask_corners(unsigned flags, const uint8_t* __restrict__ mk, const int W) {
+    if ((flags & 1u) && mk[0]) flags &= ~1u;
+    if ((flags & 2u) && mk[1]) flags &= ~2u;
+    if ((flags & 4u) && mk[W]) flags &= ~4u;
+    if ((flags & 8u) && mk[W + 1]) flags &= ~8u;
+    return flags;
 }
 
 // Sub-bin of a sample of query q whose top-left corner is (h_lo, w_lo).

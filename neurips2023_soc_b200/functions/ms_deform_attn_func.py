@@ -64,8 +64,12 @@ class MSDeformAttnFusedFunction(Function):
     (/root/reference/models/ops/modules/ms_deform_attn.py:99-106, 2-d reference points):
 
         MSDeformAttnFusedFunction.apply(value, value_spatial_shapes, value_level_start_index,
-                                        reference_points, sampling_offsets, attention_logits, im2col_step)
+                                        reference_points, sampling_offsets, attention_logits, im2col_step,
+                                        padding_mask=None)
             -> (output, sampling_locations, attention_weights)
+
+    ``padding_mask`` (bool (N, S), True on padded pixels): ``value`` is then the UNMASKED projection and the module's
+    ``value.masked_fill(mask[..., None], 0)`` (:96-97) happens inside the kernels, forward and backward.
 
     The forward kernel forms ``softmax(attention_logits)`` and ``reference_points + sampling_offsets / (W, H)``
     in its staging threads (one pass over the raw projections instead of five elementwise kernels) and writes
@@ -77,8 +81,9 @@ class MSDeformAttnFusedFunction(Function):
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
-                attention_logits, im2col_step):
+                attention_logits, im2col_step, padding_mask=None):
         ctx.im2col_step = im2col_step
+        ctx.padding_mask = padding_mask
         ctx.in_dtypes = (sampling_offsets.dtype, attention_logits.dtype, reference_points.dtype)
         # undefined gradients of the returned locations / weights must arrive as None, not as zero tensors:
         # that is how backward() knows nobody differentiated through them and takes the in-kernel chain rule
@@ -90,7 +95,7 @@ class MSDeformAttnFusedFunction(Function):
         res = msda_ext.ms_deform_attn_forward_fused(
             value, value_spatial_shapes, value_level_start_index, reference_points.float().contiguous(),
             sampling_offsets.to(raw).contiguous(), attention_logits.to(raw).contiguous(), im2col_step,
-            want_index=want_index)
+            want_index=want_index, padding_mask=padding_mask)
         output, loc, attn = res[:3]
         ctx.index = res[3] if want_index else None
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, loc, attn)
@@ -104,19 +109,24 @@ class MSDeformAttnFusedFunction(Function):
             grad_output = value.new_zeros((value.shape[0], loc.shape[1], value.shape[2] * value.shape[3]))
         go = grad_output.to(value.dtype).contiguous()
         index, ctx.index = ctx.index, None
+        mask = ctx.padding_mask
         if grad_loc_out is None and grad_attn_out is None:
             # nobody differentiated through the returned locations / weights (the encoder drops them, the decoder
             # only ranks them): the chain rule of softmax and of ref + off / (W, H) runs inside the kernel
             grad_value, grad_offsets, grad_logits = msda_ext.ms_deform_attn_backward_fused(
-                value, shapes, lsi, loc, attn, go, ctx.im2col_step, index=index)
+                value, shapes, lsi, loc, attn, go, ctx.im2col_step, index=index, padding_mask=mask)
             grad_ref = None
             if ctx.needs_input_grad[3]:
                 wh = shapes.flip(-1).to(grad_offsets.dtype)[None, None, None, :, None, :]
                 grad_ref = (grad_offsets * wh).sum(dim=(2, 4)).to(ctx.in_dtypes[2])
             return (grad_value, None, None, grad_ref, grad_offsets.to(ctx.in_dtypes[0]),
-                    grad_logits.flatten(-2).to(ctx.in_dtypes[1]), None)
+                    grad_logits.flatten(-2).to(ctx.in_dtypes[1]), None, None)
+        if mask is not None:                  # the unfused kernels know no mask: apply it around them
+            value = value.masked_fill(mask[..., None, None], 0)
         grad_value, grad_loc, grad_attn = msda_ext.ms_deform_attn_backward(
             value, shapes, lsi, loc, attn, go, ctx.im2col_step, index=index)
+        if mask is not None:
+            grad_value = grad_value.masked_fill(mask[..., None, None], 0)
         if grad_loc_out is not None:          # someone differentiated through the returned locations / weights
             grad_loc = grad_loc + grad_loc_out
         if grad_attn_out is not None:
@@ -126,4 +136,4 @@ class MSDeformAttnFusedFunction(Function):
         grad_ref = grad_loc.sum(dim=(2, 4)).to(ctx.in_dtypes[2]) if ctx.needs_input_grad[3] else None
         dot = (grad_attn * attn).sum(dim=(-1, -2), keepdim=True)
         grad_logits = (attn * (grad_attn - dot)).flatten(-2).to(ctx.in_dtypes[1])
-        return grad_value, None, None, grad_ref, grad_offsets, grad_logits, None
+        return grad_value, None, None, grad_ref, grad_offsets, grad_logits, None, None

@@ -66,15 +66,16 @@ class _EncoderLayerFunction(Function):
         q2 = x2 if pos is None else (x + pos).reshape(T, C)
         off = F.linear(q2, Wso_, cast(bso)).view(N, S, M, L, P, 2)
         logit = F.linear(q2, Waw_, cast(baw)).view(N, S, M, L * P)
-        value = F.linear(x2, Wv_, cast(bv)).view(N, S, C)
+        # the padding mask goes into the kernels (padded pixels count as zero rows; their gradient rows come back zero)
+        value = F.linear(x2, Wv_, cast(bv)).view(N, S, M, C // M)
         if pad is not None:
-            value = value.masked_fill(pad[..., None], 0.0)
-        value = value.view(N, S, M, C // M)
+            pad = pad.to(torch.bool).contiguous()
         # the encoder never looks at the sampling locations / attention weights: they are not written at all when the
         # call keeps an inverse index (many queries per frame), the backward then recomputes them from the raw projections
         raw = msda_ext.forward_index_bytes(value, off) > 0
         attn_out, loc, attn, index = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64,
-                                                                           want_index=True, materialize=not raw)
+                                                                           want_index=True, materialize=not raw,
+                                                                           padding_mask=pad)
         if raw:
             loc, attn = off, logit
         a = F.linear(attn_out.view(T, C), Wo_, cast(bo))
@@ -117,11 +118,10 @@ class _EncoderLayerFunction(Function):
         index, ctx.index = ctx.index, None
         if ctx.raw:      # loc / attn hold the raw offsets / logits
             dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ctx.ref, loc, attn, dao, 64,
-                                                                               index=index)
+                                                                               index=index, padding_mask=ctx.pad)
         else:
-            dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc, attn, dao, 64, index=index)
-        if ctx.pad is not None:
-            dvalue = dvalue.view(N, S, C).masked_fill(ctx.pad[..., None], 0.0)
+            dvalue, doff, dlogit = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc, attn, dao, 64, index=index,
+                                                                          padding_mask=ctx.pad)
         dv2 = dvalue.reshape(T, C)
         dWv = torch.mm(dv2.t(), x2)
         dbv = _colsum(dv2)

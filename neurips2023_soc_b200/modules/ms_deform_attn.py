@@ -99,20 +99,21 @@ class MSDeformAttn(nn.Module):
         M, L, P = self.n_heads, self.n_levels, self.n_points
         self._check_geometry(input_spatial_shapes, S)
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, S, M, self.d_model // M)
-
+        value = self.value_proj(input_flatten).view(N, S, M, self.d_model // M)
         offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
         logits = self.attention_weights(query).view(N, Lq, M, L * P)
 
         box = reference_points.shape[-1]
         if self.fused_prologue and msda_ext.fused_prologue_supported(value, L, P, box):
+            # the padding mask goes into the kernels too (padded pixels count as zero rows, their gradient rows are
+            # zero): no masked_fill pass over value, forward or backward
+            mask = None if input_padding_mask is None else input_padding_mask.to(torch.bool).contiguous()
             output, sampling_locations, weights = MSDeformAttnFusedFunction.apply(
                 value, input_spatial_shapes, input_level_start_index, reference_points, offsets, logits,
-                self.im2col_step)
+                self.im2col_step, mask)
             return self.output_proj(output), sampling_locations, weights
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None, None], float(0))
 
         weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         if box == 2:

@@ -165,8 +165,20 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
+def _mask_ptr(padding_mask, value):
+    """Device pointer of the (N, S) padding mask (bool / uint8, non-zero = padded pixel) or None."""
+    if padding_mask is None:
+        return None
+    _require(isinstance(padding_mask, torch.Tensor) and padding_mask.is_cuda and padding_mask.device == value.device,
+             "padding_mask must be a CUDA tensor on the device of value")
+    _require(padding_mask.dtype in (torch.bool, torch.uint8) and tuple(padding_mask.shape) == tuple(value.shape[:2])
+             and padding_mask.is_contiguous(), "padding_mask must be a contiguous bool (N, S) tensor")
+    return padding_mask.data_ptr()
+
+
 def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                                  im2col_step: int, flags: int | None = None, index=None) -> List[torch.Tensor]:
+                                  im2col_step: int, flags: int | None = None, index=None,
+                                  padding_mask=None) -> List[torch.Tensor]:
     """Backward of ``ms_deform_attn_forward_fused`` (msda_backward_fused): takes the saved fp32 sampling locations /
     attention weights and returns ``[grad_value, grad_sampling_offsets, grad_attention_logits]`` -- the chain rule
     of the module's softmax and location arithmetic is applied inside the sample-gradient kernel."""
@@ -184,7 +196,7 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, samp
         ws_bytes = int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
         _lib.check(lib.msda_backward_fused(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), _mask_ptr(padding_mask, value),
             sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
             grad_value.data_ptr(), grad_off.data_ptr(), grad_logits.data_ptr(),
             ws.data_ptr(), ws_bytes, None if index is None else index.data_ptr(),
@@ -194,8 +206,8 @@ def ms_deform_attn_backward_fused(value, spatial_shapes, level_start_index, samp
 
 
 def ms_deform_attn_backward_fused_raw(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
-                                      attn_logits, grad_output, im2col_step: int, index, flags: int | None = None
-                                      ) -> List[torch.Tensor]:
+                                      attn_logits, grad_output, im2col_step: int, index, flags: int | None = None,
+                                      padding_mask=None) -> List[torch.Tensor]:
     """Backward of ``ms_deform_attn_forward_fused(..., materialize=False)`` (msda_backward_fused_raw): takes what that
     forward took plus its index, returns ``[grad_value, grad_sampling_offsets, grad_attention_logits]`` in the dtypes
     of value / the raw projections."""
@@ -221,7 +233,8 @@ def ms_deform_attn_backward_fused_raw(value, spatial_shapes, level_start_index, 
         ws_bytes = int(lib.msda_backward_workspace_bytes(*dims, vdt, adt))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=value.device)
         _lib.check(lib.msda_backward_fused_raw(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), _mask_ptr(padding_mask, value),
+            reference_points.data_ptr(),
             sampling_offsets.data_ptr(), attn_logits.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
             grad_off.data_ptr(), grad_logits.data_ptr(), ws.data_ptr(), ws_bytes, index.data_ptr(), index.numel(),
             *dims, vdt, adt, int(im2col_step), torch.cuda.current_stream().cuda_stream,
@@ -241,10 +254,12 @@ def fused_prologue_supported(value, n_levels: int, n_points: int, ref_dim: int) 
 
 def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
                                  attn_logits, im2col_step: int, flags: int | None = None, want_index: bool = False,
-                                 materialize: bool = True):
+                                 materialize: bool = True, padding_mask=None):
     """Forward with the module's prologue fused in (msda_forward_fused): returns
     ``(output, sampling_locations fp32, attention_weights fp32[, index])``.  ``materialize=False``: the two middle
-    results are never written (returned as None); the matching backward is ``ms_deform_attn_backward_fused_raw``."""
+    results are never written (returned as None); the matching backward is ``ms_deform_attn_backward_fused_raw``.
+    ``padding_mask`` (bool (N, S), True on padded pixels): the module's ``value.masked_fill(mask[..., None], 0)``
+    applied inside the kernels -- pass the UNMASKED value and give the same mask to the backward."""
     _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("reference_points", reference_points), ("sampling_offsets", sampling_offsets),
                    ("attn_logits", attn_logits)])
@@ -271,7 +286,8 @@ def ms_deform_attn_forward_fused(value, spatial_shapes, level_start_index, refer
                 index = torch.empty(index_bytes, dtype=torch.uint8, device=value.device)
                 index_ptr = index.data_ptr()
         _lib.check(lib.msda_forward_fused(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), reference_points.data_ptr(),
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), _mask_ptr(padding_mask, value),
+            reference_points.data_ptr(),
             sampling_offsets.data_ptr(), attn_logits.data_ptr(), out.data_ptr(),
             None if loc is None else loc.data_ptr(), None if attn is None else attn.data_ptr(),
             index_ptr, index_bytes, *dims, _DTYPE[value.dtype], _DTYPE[sampling_offsets.dtype], int(im2col_step),

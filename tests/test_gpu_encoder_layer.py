@@ -208,3 +208,55 @@ def test_raw_fused_backward_matches_materialised_one(vdt, adt):
     with pytest.raises(RuntimeError):          # a decoder-shaped call keeps no index: not this entry point
         msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ref[:, :5].contiguous(), off[:, :5].contiguous(),
                                                    logit[:, :5].contiguous(), go[:, :5].contiguous(), 64, index=idx_b)
+
+
+@pytest.mark.parametrize("vdt,adt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("Lq", [None, 20])
+def test_padding_mask_inside_the_kernels_equals_masked_fill(vdt, adt, Lq):
+    """The module's value.masked_fill(padding_mask, 0) (ms_deform_attn.py:96-97) applied inside the kernels -- padded
+    pixels dropped corner by corner in the forward and the sample-gradient kernel, their grad_value rows zeroed by the
+    walker / the direct gather -- against masked_fill around the same kernels: the same bits, for encoder-shaped calls
+    (inverse index; materialising and raw backward) and decoder-shaped ones (Lq = 20: direct gather)."""
+    g = torch.Generator().manual_seed(13)
+    shapes_l = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in shapes_l)
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    shapes = torch.tensor(shapes_l, dtype=torch.long, device=DEV)
+    lsi = torch.tensor(level_start_index(shapes_l), dtype=torch.long, device=DEV)
+    value = torch.randn(N, S, M, D, generator=g).to(DEV, vdt)
+    mask = (torch.rand(N, S, generator=g) < 0.3).to(DEV)                 # a third of the pixels are padding
+    mask[0, :40] = True                                                  # whole rows of the finest level too
+    nq = S if Lq is None else Lq
+    if Lq is None:
+        ref = DeformableTransformerEncoder.get_reference_points(shapes_l, torch.ones(N, L, 2, device=DEV), DEV).contiguous()
+    else:
+        ref = torch.rand(N, nq, L, 2, generator=g).to(DEV)
+    off = (torch.randn(N, nq, M, L, P, 2, generator=g) * 3).to(DEV, adt)
+    logit = torch.randn(N, nq, M, L * P, generator=g).to(DEV, adt)
+    go = torch.randn(N, nq, M * D, generator=g).to(DEV, vdt)
+    filled = value.masked_fill(mask[..., None, None], 0)
+
+    out_m, loc_m, attn_m, idx_m = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64, want_index=True,
+                                                                        padding_mask=mask)
+    out_f, loc_f, attn_f, idx_f = msda_ext.ms_deform_attn_forward_fused(filled, shapes, lsi, ref, off, logit, 64, want_index=True)
+    assert torch.equal(out_m, out_f) and torch.equal(loc_m, loc_f) and torch.equal(attn_m, attn_f)
+    gm = msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, loc_m, attn_m, go, 64, index=idx_m, padding_mask=mask)
+    gf = msda_ext.ms_deform_attn_backward_fused(filled, shapes, lsi, loc_f, attn_f, go, 64, index=idx_f)
+    gf[0] = gf[0].masked_fill(mask[..., None, None], 0)                  # masked_fill's own backward
+    for a, b in zip(gm, gf):
+        assert torch.equal(a, b)
+    assert float(gm[0][mask].abs().max()) == 0.0
+    if Lq is None:                                                       # the raw pair (what the encoder layer runs)
+        out_r, _, _, idx_r = msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64, want_index=True,
+                                                                   materialize=False, padding_mask=mask)
+        assert torch.equal(out_r, out_f)
+        gr = msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ref, off, logit, go, 64, index=idx_r, padding_mask=mask)
+        gfr = msda_ext.ms_deform_attn_backward_fused_raw(filled, shapes, lsi, ref, off, logit, go, 64,
+                                                         index=msda_ext.ms_deform_attn_forward_fused(
+                                                             filled, shapes, lsi, ref, off, logit, 64, want_index=True,
+                                                             materialize=False)[3])
+        gfr[0] = gfr[0].masked_fill(mask[..., None, None], 0)
+        for a, b in zip(gr, gfr):
+            assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="padding_mask"):
+        msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64, padding_mask=mask[:, :-1])

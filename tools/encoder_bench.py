@@ -81,6 +81,8 @@ def main():
     ap.add_argument("--reference-module", action="store_true", help="keep the reference's own MSDeformAttn module / autograd function too")
     ap.add_argument("--graph", action="store_true", help="capture the whole training step (forward, backward, AdamW) in a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="print the step's CUDA kernels by total time (torch.profiler)")
+    ap.add_argument("--pad", action="store_true",
+                    help="pass a padding mask (all False, as for A2D's equal-size frames: models/soc.py always passes one)")
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
@@ -101,6 +103,7 @@ def main():
     ref = pyramid_reference_points(shapes_l).to(dev)[None, :, None, :].expand(a.frames, S, len(shapes_l), 2).contiguous()
     src = torch.randn(a.frames, S, 256, device=dev)
     pos = torch.randn(a.frames, S, 256, device=dev)
+    padmask = torch.zeros(a.frames, S, dtype=torch.bool, device=dev) if a.pad else None
     model = None if (a.restated or a.b200_layers) else reference_encoder(a.layers, a.reference_module)
     which = "reference DeformableTransformerEncoder (staged, unmodified)" + (" + reference MSDeformAttn module" if a.reference_module else "")
     if a.b200_layers:
@@ -108,13 +111,13 @@ def main():
         model = DeformableTransformerEncoder(DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4), a.layers)
         which = "neurips2023_soc_b200.DeformableTransformerEncoder (fused layers, bf16 end to end)"
         ratios = torch.ones(a.frames, len(shapes_l), 2, device=dev)
-        call = lambda net: net(src, shapes, lsi, ratios, pos, None)                           # noqa: E731
+        call = lambda net: net(src, shapes, lsi, ratios, pos, padmask)                        # noqa: E731
     elif model is None:
         model, which = Encoder(a.layers), "restated encoder"
         call = lambda net: net(src, pos, ref, shapes, lsi)                                    # noqa: E731
     else:
         ratios = torch.ones(a.frames, len(shapes_l), 2, device=dev)                           # no padding: valid ratio 1
-        call = lambda net: net(src, shapes, lsi, ratios, pos, None)                           # noqa: E731
+        call = lambda net: net(src, shapes, lsi, ratios, pos, padmask)                        # noqa: E731
     model = model.to(dev)
     with torch.no_grad():          # leave the all-zero init of the offset / attention projections
         for m in model.modules():
@@ -184,7 +187,7 @@ def main():
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90), file=sys.stderr)
     if rank == 0:
         print(json.dumps({"what": "deformable encoder fwd+bwd+AdamW", "encoder": which, "layers": a.layers, "frames_per_gpu": a.frames,
-                          "tokens_per_frame": S, "amp_bf16": a.amp, "fused_prologue": a.fuse, "cuda_graph": a.graph, "n_gpus": world, "ms_per_step": float(ms.item()),
+                          "tokens_per_frame": S, "amp_bf16": a.amp, "padding_mask": bool(a.pad), "fused_prologue": a.fuse, "cuda_graph": a.graph, "n_gpus": world, "ms_per_step": float(ms.item()),
                           "queries_per_s": world * a.frames * S / (float(ms.item()) * 1e-3),
                           "msda_kernels_ms_per_step": fwd_ms, "loss": float(loss.detach())}))
     if world > 1:
