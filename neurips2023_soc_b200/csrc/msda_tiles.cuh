@@ -169,7 +169,9 @@ __device__ __forceinline__ void stage_build(Staged<TileShape<G>::DPT>& st, const
                 const unsigned h0 = s.h_lo >= 0, w0 = s.w_lo >= 0;
                 const unsigned h1 = s.h_lo + 1 <= L_.H - 1, w1 = s.w_lo + 1 <= L_.W - 1;
                 unsigned flags = (h0 & w0) | ((h0 & w1) << 1) | ((h1 & w0) << 2) | ((h1 & w1) << 3);
-                if (p.value_mask != nullptr)      // padded pixels hold zeros (the module's masked_fill, fused)
+                // padded pixels hold zeros (the module's masked_fill, fused); the mask only arrives through the fused
+                // entry points, i.e. in the FUSED forward and the chain-rule (KEEPW) backward instances
+                if ((FUSED || KEEPW) && p.value_mask != nullptr)
                     flags = mask_corners(flags, p.value_mask + (size_t)tl.n * p.S + L_.start + s.h_lo * L_.W + s.w_lo, L_.W);
                 d.x = (flags << 28) | (unsigned)((s.h_lo + 1) * L_.W + (s.w_lo + 1));
                 d.y = __float_as_uint(s.lh);
