@@ -45,11 +45,13 @@ class MSDeformAttn(nn.Module):
                           "for bf16) takes the 128-bit tile kernels; other sizes use the generic kernels.")
         self.im2col_step = 64
         self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
-        #: True: run softmax + location arithmetic inside the forward kernel when a kernel exists for the
-        #: shape (MSDeformAttnFusedFunction).  Opt-in: measured neutral at the encoder level this round (the
-        #: heavier staging of the forward kernel costs what the three elementwise kernels it replaces cost);
-        #: it does keep offset / (W, H) in fp32 under autocast, where the stock sequence rounds it to bf16.
-        self.fused_prologue = False
+        #: True (default): softmax, location arithmetic and the padding masked_fill run inside the kernels, forward and
+        #: backward, whenever a kernel exists for the shape (MSDeformAttnFusedFunction; anything else takes the
+        #: reference's elementwise sequence below).  Measured on the 3-layer A2D encoder step under bf16 autocast:
+        #: 13.6 -> 12.6 ms, 14.0 -> 12.8 ms with a padding mask.  It also keeps
+        #: offset / (W, H) in fp32 under autocast, where the stock sequence rounds it to bf16.  False: always the
+        #: elementwise sequence.
+        self.fused_prologue = True
 
         samples = n_heads * n_levels * n_points
         self.sampling_offsets = nn.Linear(d_model, 2 * samples)
