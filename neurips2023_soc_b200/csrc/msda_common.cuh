@@ -55,7 +55,7 @@ struct Params {
                              //                    (scan) -> its end offset (fill); readers use row[b], row[b+1]
     void* entries;           // [N*M][Lq*L*P]      per-bin contribution lists
     uint32_t* counts;        // [0] entries in big_bins (right behind bin_off so one memset clears both)
-    uint32_t* big_bins;      // (nm, sub-bin) pairs of sub-bins with > 32 entries
+    uint32_t* big_bins;      // (nm, sub-bin) pairs of sub-bins with > kRankMax entries
     int N, S, M, D, L, Lq, P;
     int LP;                  // L*P
     int id_shift;            // entry id = (q << id_shift) | s,  1<<id_shift >= LP
