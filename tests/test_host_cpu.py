@@ -163,3 +163,30 @@ def test_bench_own_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a GPU is present")
     rc, lines, _, err = _run_bench("--steps", "1")
     assert rc != 0 and not lines and "no CPU fallback" in err
+
+
+def test_fused_entry_points_refuse_cpu_tensors_and_bad_masks():
+    """The fused prologue / encoder-layer entry points of the shim have the reference's error behaviour too: CPU
+    tensors are refused before anything is launched (there is no CPU path), and so is a malformed padding mask."""
+    N, S, M, D, L, P, Lq = 1, 6, 2, 32, 1, 4, 3
+    value = torch.zeros(N, S, M, D)
+    shapes = torch.tensor([[2, 3]], dtype=torch.long)
+    lsi = torch.tensor([0], dtype=torch.long)
+    ref = torch.zeros(N, Lq, L, 2)
+    off = torch.zeros(N, Lq, M, L, P, 2)
+    logit = torch.zeros(N, Lq, M, L * P)
+    go = torch.zeros(N, Lq, M * D)
+    with pytest.raises(RuntimeError, match="CUDA tensor|Not implemented on the CPU"):
+        msda_ext.ms_deform_attn_forward_fused(value, shapes, lsi, ref, off, logit, 64)
+    with pytest.raises(RuntimeError, match="CUDA tensor|Not implemented on the CPU"):
+        msda_ext.ms_deform_attn_backward_fused(value, shapes, lsi, off, logit.view(N, Lq, M, L, P), go, 64)
+    with pytest.raises(RuntimeError, match="CUDA tensor|Not implemented on the CPU"):
+        msda_ext.ms_deform_attn_backward_fused_raw(value, shapes, lsi, ref, off, logit, go, 64, index=torch.zeros(16, dtype=torch.uint8))
+    x = torch.zeros(4, 256)
+    assert not msda_ext.add_layernorm_supported(x)                      # CPU rows: the caller keeps torch's LayerNorm
+    with pytest.raises(RuntimeError, match="CUDA tensor|Not implemented on the CPU"):
+        msda_ext.add_layernorm_forward(x, x.clone(), torch.ones(256), torch.zeros(256))
+    with pytest.raises(RuntimeError, match="padding_mask"):
+        msda_ext._mask_ptr(torch.zeros(N, S, dtype=torch.bool), value)  # a mask must live on the device of value
+    assert msda_ext._mask_ptr(None, value) is None
+    assert not msda_ext.fused_prologue_supported(value, L, P, 2)        # CPU value: the module keeps the elementwise sequence
